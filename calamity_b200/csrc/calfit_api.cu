@@ -1,0 +1,1146 @@
+// Host side of libcalamity_b200: plan construction, uploads, the fit loop and the C ABI of
+// include/calamity_b200.h.  No torch types, no exceptions across the boundary.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/calamity_b200.h"
+#include "calfit_kernels.cuh"
+#include "calfit_setup.cuh"
+
+namespace calb2 {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(CALB2_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+static constexpr int RPT = 11;
+static constexpr int NWARP = 8;
+static constexpr int SMAX = 8;
+
+// ---- NCCL through dlopen (the library has no link-time dependency on it) -------------------------
+struct IdBlob {
+  char bytes[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ IdBlob, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl(const char* path) {
+  if (g_nccl.handle) return 0;
+  const char* cands[] = {path, "libnccl.so.2", "libnccl.so"};
+  for (const char* c : cands) {
+    if (!c || !*c) continue;
+    g_nccl.handle = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) return fail(CALB2_ERR_NCCL, "cannot dlopen NCCL (%s)", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.handle, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.handle, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.handle, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.handle, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+    return fail(CALB2_ERR_NCCL, "NCCL symbols missing");
+  return 0;
+}
+static constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+}  // namespace calb2
+
+using namespace calb2;
+
+struct calb2_plan {
+  int device = 0, nants = 0, nf = 0, ngroups = 0;
+  int FL = 0, G = 0, FT = 0, KMAX = 0, nfp = 0, ntiles = 0;
+  long long nbls = 0, nslots = 0, ncoef = 0, rows_total = 0, a_floats = 0, n_a_nz = 0;
+  // host copies of the description
+  std::vector<int> grp_ncomp, grp_nslots, grp_slot0, grp_coef0, slot_nbls, slot_grp, slot_row0, slot_bl0, slot_item,
+      bl_ant0, bl_ant1, bl_slot;
+  std::vector<ItemDesc> items;
+  // device
+  DevBuf<float> A, d_r, d_i, w, g_r[2], g_i[2], gm_r, gu_r, gm_i, gu_i, gsnap_r, gsnap_i, ggrad_r, ggrad_i;
+  DevBuf<float> c_r, c_i, cm_r, cu_r, cm_i, cu_i, csnap_r, csnap_i, cgrad_r, cgrad_i, dcpart, hist, scratch_f;
+  DevBuf<float2> z, y, vout;
+  DevBuf<double> partials, red_d;
+  DevBuf<ItemDesc> d_items;
+  DevBuf<unsigned char> row_slot;
+  DevBuf<int> row_coef, d_slot_row0, d_slot_bl0, d_bl_ant0, d_bl_ant1, d_bl_slot, ant_ptr, ant_ent, coef_row0, coef_grp,
+      d_grp_nslots, d_grp_slot0, d_grp_coef0, d_grp_ncomp;
+  DevBuf<FitState> state, state_eval;
+  DevBuf<SlotGeom> slot_geom;
+  DevBuf<float> sky_r, sky_i;
+  DevBuf<float> staging;
+  float* h_staging = nullptr;
+  size_t staging_floats = 0;
+  FitState* h_state = nullptr;  // pinned
+  cudaStream_t stream = nullptr;
+  int cur_buf = 0;
+  bool have_data = false, have_gains = false, have_coeffs = false, basis_complete = false;
+  long long basis_groups_set = 0;
+  // comm
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+  DevBuf<double> comm_scalars;
+  size_t device_bytes = 0;
+};
+
+namespace calb2 {
+
+template <class T>
+static int upload(DevBuf<T>& buf, const std::vector<T>& v, calb2_plan* pl) {
+  CU(buf.alloc(v.size()));
+  pl->device_bytes += buf.bytes();
+  if (!v.empty()) CU(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+template <class T>
+static int dalloc(DevBuf<T>& buf, size_t n, calb2_plan* pl, bool zero = true) {
+  CU(buf.alloc(n));
+  pl->device_bytes += buf.bytes();
+  if (zero && n) CU(cudaMemset(buf.p, 0, buf.bytes()));
+  return 0;
+}
+
+static int choose_fl(const calb2_plan_desc* d, int* fl_out) {
+  int maxc = 0;
+  for (int g = 0; g < d->ngroups; ++g) maxc = std::max(maxc, d->group_ncomp[g]);
+  const int cands[3] = {16, 8, 4};
+  if (d->tile_freqs) {
+    const int fl = d->tile_freqs / 4;
+    if (d->tile_freqs % 4 || (fl != 16 && fl != 8 && fl != 4)) return fail(CALB2_ERR_ARG, "tile_freqs must be 16, 32 or 64");
+    const int G = 32 / fl;
+    if (((maxc + G - 1) / G) * G > NWARP * RPT * G)
+      return fail(CALB2_ERR_UNSUPPORTED, "a group has %d basis vectors; tile_freqs=%d stages at most %d", maxc,
+                  d->tile_freqs, NWARP * RPT * G);
+    *fl_out = fl;
+    return 0;
+  }
+  for (int fl : cands) {
+    const int G = 32 / fl;
+    if (((maxc + G - 1) / G) * G <= NWARP * RPT * G) {
+      *fl_out = fl;
+      return 0;
+    }
+  }
+  return fail(CALB2_ERR_UNSUPPORTED, "a group has %d basis vectors; at most %d are supported", maxc, NWARP * RPT * 8);
+}
+
+template <int FL, bool SUM>
+static cudaError_t launch_heavy_t(const HeavyParams& hp, int nitems, cudaStream_t s) {
+  using C = HeavyCfg<FL, SUM, RPT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(heavy_kernel<FL, SUM, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  heavy_kernel<FL, SUM, RPT><<<nitems, C::NTHR, C::SMEM_BYTES, s>>>(hp);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_heavy(int FL, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
+  switch (FL) {
+    case 16: return sum ? launch_heavy_t<16, true>(hp, nitems, s) : launch_heavy_t<16, false>(hp, nitems, s);
+    case 8: return sum ? launch_heavy_t<8, true>(hp, nitems, s) : launch_heavy_t<8, false>(hp, nitems, s);
+    default: return sum ? launch_heavy_t<4, true>(hp, nitems, s) : launch_heavy_t<4, false>(hp, nitems, s);
+  }
+}
+
+static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, int store_v, int init_mode) {
+  HeavyParams hp{};
+  hp.A = pl->A.p;
+  hp.items = pl->d_items.p;
+  hp.row_slot = pl->row_slot.p;
+  hp.row_coef = pl->row_coef.p;
+  hp.slot_row0 = pl->d_slot_row0.p;
+  hp.slot_bl0 = pl->d_slot_bl0.p;
+  hp.bl_ant0 = pl->d_bl_ant0.p;
+  hp.bl_ant1 = pl->d_bl_ant1.p;
+  hp.d_r = pl->d_r.p;
+  hp.d_i = pl->d_i.p;
+  hp.w = pl->w.p;
+  for (int b = 0; b < 2; ++b) {
+    hp.g_r[b] = pl->g_r[b].p;
+    hp.g_i[b] = pl->g_i[b].p;
+  }
+  hp.c_r = pl->c_r.p;
+  hp.c_i = pl->c_i.p;
+  hp.z = pl->z.p;
+  hp.y = sum ? pl->y.p : nullptr;
+  hp.dcpart = pl->dcpart.p;
+  hp.vout = pl->vout.p;
+  hp.partials = pl->partials.p;
+  hp.st = st;
+  hp.nfp = pl->nfp;
+  hp.ntiles = pl->ntiles;
+  hp.store_v = store_v;
+  hp.init_mode = init_mode;
+  return hp;
+}
+
+static GainsParams gains_params(calb2_plan* pl, const FitState* st, const FitConsts& k, int mode, bool sum, int eval) {
+  GainsParams gp{};
+  gp.z = pl->z.p;
+  gp.y = pl->y.p;
+  gp.ant_ptr = pl->ant_ptr.p;
+  gp.ant_ent = pl->ant_ent.p;
+  gp.bl_ant0 = pl->d_bl_ant0.p;
+  gp.bl_ant1 = pl->d_bl_ant1.p;
+  for (int b = 0; b < 2; ++b) {
+    gp.g_r[b] = pl->g_r[b].p;
+    gp.g_i[b] = pl->g_i[b].p;
+  }
+  gp.m_r = pl->gm_r.p;
+  gp.u_r = pl->gu_r.p;
+  gp.m_i = pl->gm_i.p;
+  gp.u_i = pl->gu_i.p;
+  gp.snap_r = k.use_min ? pl->gsnap_r.p : nullptr;
+  gp.snap_i = k.use_min ? pl->gsnap_i.p : nullptr;
+  gp.grad_r = (mode != 0) ? pl->ggrad_r.p : nullptr;
+  gp.grad_i = (mode != 0) ? pl->ggrad_i.p : nullptr;
+  gp.st = st;
+  gp.k = k;
+  gp.nfp = pl->nfp;
+  gp.nants = pl->nants;
+  gp.mode = mode;
+  gp.sum = sum ? 1 : 0;
+  gp.eval = eval;
+  return gp;
+}
+
+static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitConsts& k, int mode, bool sum) {
+  CoeffParams cp{};
+  cp.dcpart = pl->dcpart.p;
+  cp.coef_row0 = pl->coef_row0.p;
+  cp.coef_grp = pl->coef_grp.p;
+  cp.grp_nslots = pl->d_grp_nslots.p;
+  cp.grp_slot0 = pl->d_grp_slot0.p;
+  cp.grp_coef0 = pl->d_grp_coef0.p;
+  cp.slot_row0 = pl->d_slot_row0.p;
+  cp.c_r = pl->c_r.p;
+  cp.c_i = pl->c_i.p;
+  cp.m_r = pl->cm_r.p;
+  cp.u_r = pl->cu_r.p;
+  cp.m_i = pl->cm_i.p;
+  cp.u_i = pl->cu_i.p;
+  cp.snap_r = k.use_min ? pl->csnap_r.p : nullptr;
+  cp.snap_i = k.use_min ? pl->csnap_i.p : nullptr;
+  cp.grad_r = (mode == 1) ? pl->cgrad_r.p : nullptr;
+  cp.grad_i = (mode == 1) ? pl->cgrad_i.p : nullptr;
+  cp.st = st;
+  cp.k = k;
+  cp.ncoef = (int)pl->ncoef;
+  cp.nq = sum ? 4 : 2;
+  cp.mode = mode;
+  return cp;
+}
+
+static int ensure_use_min_buffers(calb2_plan* pl) {
+  if (!pl->gsnap_r.p) {
+    if (int r = dalloc(pl->gsnap_r, (size_t)pl->nants * pl->nfp, pl)) return r;
+    if (int r = dalloc(pl->gsnap_i, (size_t)pl->nants * pl->nfp, pl)) return r;
+    if (int r = dalloc(pl->csnap_r, (size_t)pl->ncoef, pl)) return r;
+    if (int r = dalloc(pl->csnap_i, (size_t)pl->ncoef, pl)) return r;
+  }
+  return 0;
+}
+static int ensure_sum_buffers(calb2_plan* pl) {
+  if (!pl->y.p) return dalloc(pl->y, (size_t)pl->nbls * pl->nfp, pl);
+  return 0;
+}
+static int ensure_grad_buffers(calb2_plan* pl) {
+  if (!pl->ggrad_r.p) {
+    if (int r = dalloc(pl->ggrad_r, (size_t)pl->nants * pl->nfp, pl)) return r;
+    if (int r = dalloc(pl->ggrad_i, (size_t)pl->nants * pl->nfp, pl)) return r;
+  }
+  if (!pl->cgrad_r.p) {
+    if (int r = dalloc(pl->cgrad_r, (size_t)pl->ncoef, pl)) return r;
+    if (int r = dalloc(pl->cgrad_i, (size_t)pl->ncoef, pl)) return r;
+  }
+  return 0;
+}
+static int ensure_vout(calb2_plan* pl) {
+  if (!pl->vout.p) return dalloc(pl->vout, (size_t)pl->nslots * pl->nfp, pl);
+  return 0;
+}
+
+// host [n][nf] -> device [n][nfp] through the pinned staging buffer
+static int upload_padded(calb2_plan* pl, const float* src, float* dst, size_t nrows, float fill) {
+  const size_t rows_per = std::max<size_t>(1, pl->staging_floats / (size_t)pl->nf);
+  for (size_t r0 = 0; r0 < nrows; r0 += rows_per) {
+    const size_t n = std::min(rows_per, nrows - r0);
+    memcpy(pl->h_staging, src + r0 * pl->nf, n * pl->nf * sizeof(float));
+    CU(cudaMemcpyAsync(pl->staging.p, pl->h_staging, n * pl->nf * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+    pad_rows_kernel<<<(unsigned)n, 128, 0, pl->stream>>>(pl->staging.p, dst + r0 * pl->nfp, pl->nf, pl->nfp, fill);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(pl->stream));
+  }
+  return 0;
+}
+static int download_unpadded(calb2_plan* pl, const float* src, float* dst, size_t nrows) {
+  const size_t rows_per = std::max<size_t>(1, pl->staging_floats / (size_t)pl->nf);
+  for (size_t r0 = 0; r0 < nrows; r0 += rows_per) {
+    const size_t n = std::min(rows_per, nrows - r0);
+    unpad_rows_kernel<<<(unsigned)n, 128, 0, pl->stream>>>(src + r0 * pl->nfp, pl->staging.p, pl->nf, pl->nfp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pl->h_staging, pl->staging.p, n * pl->nf * sizeof(float), cudaMemcpyDeviceToHost, pl->stream));
+    CU(cudaStreamSynchronize(pl->stream));
+    memcpy(dst + r0 * pl->nf, pl->h_staging, n * pl->nf * sizeof(float));
+  }
+  return 0;
+}
+
+static int set_eval_state(calb2_plan* pl) {
+  FitState s{};
+  s.step = pl->cur_buf;
+  s.stop_after = INT_MAX;
+  s.upd_active = 0;
+  CU(cudaMemcpyAsync(pl->state_eval.p, &s, sizeof(s), cudaMemcpyHostToDevice, pl->stream));
+  return 0;
+}
+
+static int all_reduce(calb2_plan* pl, void* buf, size_t count, int dtype) {
+  if (pl->nranks <= 1) return 0;
+  int rc = g_nccl.AllReduce(buf, buf, count, dtype, NCCL_SUM, pl->comm, pl->stream);
+  if (rc != 0) return fail(CALB2_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return 0;
+}
+
+// One optimizer iteration (calibration.py:663-668) enqueued on the plan's stream.
+static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freeze, float* hist, cudaEvent_t ev0,
+                        cudaEvent_t ev1, long long* launches) {
+  HeavyParams hp = heavy_params(pl, pl->state.p, sum, 0, 0);
+  if (ev0) CU(cudaEventRecord(ev0, pl->stream));
+  CU(launch_heavy(pl->FL, sum, hp, (int)pl->items.size(), pl->stream));
+  if (ev1) CU(cudaEventRecord(ev1, pl->stream));
+  FinalizeParams fp{};
+  fp.st = pl->state.p;
+  fp.k = k;
+  fp.hist = hist;
+  fp.eval_only = 0;
+  if (pl->nranks > 1) {
+    reduce_partials_kernel<<<1, 1024, 0, pl->stream>>>(pl->partials.p, (int)pl->items.size(), pl->comm_scalars.p);
+    CU(cudaGetLastError());
+    if (int r = all_reduce(pl, pl->comm_scalars.p, 4, NCCL_FLOAT64)) return r;
+    fp.partials = pl->comm_scalars.p;
+    fp.nitems = 1;
+    *launches += 1;
+  } else {
+    fp.partials = pl->partials.p;
+    fp.nitems = (int)pl->items.size();
+  }
+  finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
+  CU(cudaGetLastError());
+  dim3 ggrid((pl->nfp + 127) / 128, pl->nants);
+  if (pl->nranks > 1) {
+    gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 1, sum, 0));
+    CU(cudaGetLastError());
+    // real and imaginary gradient tables are adjacent halves of one allocation
+    if (int r = all_reduce(pl, pl->ggrad_r.p, (size_t)2 * pl->nants * pl->nfp, NCCL_FLOAT32)) return r;
+    gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 2, sum, 0));
+    CU(cudaGetLastError());
+    *launches += 1;
+  } else {
+    gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 0, sum, 0));
+    CU(cudaGetLastError());
+  }
+  if (!freeze || k.use_min) {
+    coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(
+        coeff_params(pl, pl->state.p, k, freeze ? 3 : 0, sum));
+    CU(cudaGetLastError());
+    *launches += 1;
+  }
+  *launches += 3;
+  return 0;
+}
+
+
+// tensorize_fg_coeffs on the device (calibration.py:828-913), real and imaginary parts in one go.
+static int init_coeffs_impl(calb2_plan* pl, const float* sky_r, const float* sky_i) {
+  const size_t nd = (size_t)pl->nbls * pl->nfp;
+  if (pl->sky_r.n < nd) {
+    if (int r = dalloc(pl->sky_r, nd, pl)) return r;
+    if (int r = dalloc(pl->sky_i, nd, pl)) return r;
+  }
+  if (int r = ensure_grad_buffers(pl)) return r;
+  if (int r = upload_padded(pl, sky_r, pl->sky_r.p, (size_t)pl->nbls, 0.f)) return r;
+  if (int r = upload_padded(pl, sky_i, pl->sky_i.p, (size_t)pl->nbls, 0.f)) return r;
+  if (int r = set_eval_state(pl)) return r;
+  // right-hand sides A^T (sky * (w != 0)) through the fused kernel's backward contraction
+  HeavyParams hp = heavy_params(pl, pl->state_eval.p, false, 0, 1);
+  hp.d_r = pl->sky_r.p;
+  hp.d_i = pl->sky_i.p;
+  CU(launch_heavy(pl->FL, false, hp, (int)pl->items.size(), pl->stream));
+  FitConsts k{};
+  coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(coeff_params(pl, pl->state_eval.p, k, 1, false));
+  CU(cudaGetLastError());
+  // Gram + Cholesky per group, in batches bounded by the scratch budget
+  const size_t budget = (size_t)48 << 20;  // doubles (384 MiB)
+  DevBuf<double> gram;
+  DevBuf<GramJob> djobs;
+  std::vector<GramJob> jobs;
+  size_t used = 0;
+  int maxn = 0;
+  auto flush = [&]() -> int {
+    if (jobs.empty()) return 0;
+    if (gram.n < used) CU(gram.alloc(std::max(used, budget)));
+    if (djobs.n < jobs.size()) CU(djobs.alloc(jobs.size() * 2));
+    CU(cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(GramJob), cudaMemcpyHostToDevice, pl->stream));
+    constexpr int FC = 32;
+    const size_t smem = (size_t)maxn * (FC + 1) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+      CU(cudaFuncSetAttribute(gram_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 << 10)));
+      configured = smem;
+    }
+    gram_kernel<FC><<<(unsigned)jobs.size(), 256, smem, pl->stream>>>(pl->A.p, djobs.p, pl->slot_geom.p, gram.p, pl->nf, pl->FT);
+    CU(cudaGetLastError());
+    chol_solve_kernel<<<(unsigned)jobs.size(), 256, 0, pl->stream>>>(djobs.p, gram.p, pl->cgrad_r.p, pl->cgrad_i.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(pl->stream));
+    jobs.clear();
+    used = 0;
+    maxn = 0;
+    return 0;
+  };
+  for (int g = 0; g < pl->ngroups; ++g) {
+    const int n = pl->grp_ncomp[g];
+    if (n == 0) continue;
+    const size_t need = (size_t)n * n + 2 * (size_t)n;
+    if (used + need > budget && !jobs.empty())
+      if (int r = flush()) return r;
+    GramJob jb{};
+    jb.gram_off = (long long)used;
+    jb.grp = g;
+    jb.n = n;
+    jb.slot0 = pl->grp_slot0[g];
+    jb.nslots = pl->grp_nslots[g];
+    jb.coef0 = pl->grp_coef0[g];
+    jobs.push_back(jb);
+    used += need;
+    maxn = std::max(maxn, n);
+  }
+  if (int r = flush()) return r;
+  gram.release();
+  djobs.release();
+  CU(cudaMemcpyAsync(pl->c_r.p, pl->cgrad_r.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+  CU(cudaMemcpyAsync(pl->c_i.p, pl->cgrad_i.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+  CU(cudaStreamSynchronize(pl->stream));
+  pl->have_coeffs = true;
+  return 0;
+}
+
+}  // namespace calb2
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+extern "C" {
+
+const char* calb2_last_error(void) { return g_err.c_str(); }
+const char* calb2_version(void) { return "calamity_b200 0.1 (sm_100a)"; }
+
+int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
+  if (!d || !out) return fail(CALB2_ERR_ARG, "null argument");
+  if (d->nants <= 0 || d->nfreqs <= 0 || d->ngroups <= 0) return fail(CALB2_ERR_ARG, "empty problem");
+  int fl = 0;
+  if (int r = choose_fl(d, &fl)) return r;
+  CU(cudaSetDevice(d->device));
+  calb2_plan* pl = new calb2_plan();
+  pl->device = d->device;
+  pl->nants = d->nants;
+  pl->nf = d->nfreqs;
+  pl->ngroups = d->ngroups;
+  pl->FL = fl;
+  pl->G = 32 / fl;
+  pl->FT = 4 * fl;
+  pl->KMAX = NWARP * RPT * pl->G;
+  pl->ntiles = (pl->nf + pl->FT - 1) / pl->FT;
+  pl->nfp = pl->ntiles * pl->FT;
+  const int G = pl->G;
+
+  // ---- flatten groups -> slots -> baselines ----
+  pl->grp_ncomp.assign(d->group_ncomp, d->group_ncomp + d->ngroups);
+  pl->grp_nslots.assign(d->group_nslots, d->group_nslots + d->ngroups);
+  pl->grp_slot0.resize(d->ngroups);
+  pl->grp_coef0.resize(d->ngroups);
+  long long ns = 0, nc = 0;
+  for (int g = 0; g < d->ngroups; ++g) {
+    if (d->group_ncomp[g] < 0 || d->group_nslots[g] <= 0) {
+      delete pl;
+      return fail(CALB2_ERR_ARG, "group %d: bad ncomp/nslots", g);
+    }
+    pl->grp_slot0[g] = (int)ns;
+    pl->grp_coef0[g] = (int)nc;
+    ns += d->group_nslots[g];
+    nc += d->group_ncomp[g];
+  }
+  pl->nslots = ns;
+  pl->ncoef = nc;
+  pl->slot_nbls.assign(d->slot_nbls, d->slot_nbls + ns);
+  pl->slot_grp.resize(ns);
+  pl->slot_bl0.resize(ns + 1);
+  long long nb = 0;
+  for (int g = 0; g < d->ngroups; ++g)
+    for (int s = 0; s < d->group_nslots[g]; ++s) pl->slot_grp[pl->grp_slot0[g] + s] = g;
+  for (long long s = 0; s < ns; ++s) {
+    pl->slot_bl0[s] = (int)nb;
+    nb += pl->slot_nbls[s];
+  }
+  pl->slot_bl0[ns] = (int)nb;
+  pl->nbls = nb;
+  pl->bl_ant0.assign(d->bl_ant0, d->bl_ant0 + nb);
+  pl->bl_ant1.assign(d->bl_ant1, d->bl_ant1 + nb);
+  for (long long b = 0; b < nb; ++b)
+    if (pl->bl_ant0[b] < 0 || pl->bl_ant0[b] >= d->nants || pl->bl_ant1[b] < 0 || pl->bl_ant1[b] >= d->nants) {
+      delete pl;
+      return fail(CALB2_ERR_ARG, "baseline %lld: antenna index out of range", b);
+    }
+  pl->bl_slot.resize(nb);
+  for (long long s = 0; s < ns; ++s)
+    for (int b = pl->slot_bl0[s]; b < pl->slot_bl0[s + 1]; ++b) pl->bl_slot[b] = (int)s;
+
+  // ---- pack slots into items (one CTA each): rows <= KMAX, slots <= SMAX ----
+  pl->slot_row0.resize(ns + 1);
+  pl->slot_item.resize(ns);
+  std::vector<unsigned char> row_slot;
+  std::vector<int> row_coef;
+  ItemDesc cur{};
+  cur.nrows = 0;
+  cur.nslots = 0;
+  long long rows = 0, a_off = 0;
+  auto close_item = [&]() {
+    if (cur.nslots == 0) return;
+    pl->items.push_back(cur);
+    a_off += (long long)cur.nrows * pl->nfp;
+    cur = ItemDesc{};
+  };
+  for (long long s = 0; s < ns; ++s) {
+    const int g = pl->slot_grp[s];
+    const int ncomp = pl->grp_ncomp[g];
+    const int rp = std::max(G, ((ncomp + G - 1) / G) * G);  // at least one step so the slot exists in the item
+    if (cur.nslots > 0 && (cur.nrows + rp > pl->KMAX || cur.nslots >= SMAX)) close_item();
+    if (cur.nslots == 0) {
+      cur.a_off = a_off;
+      cur.row0 = (int)rows;
+      cur.slot0 = (int)s;
+    }
+    pl->slot_row0[s] = (int)rows;
+    pl->slot_item[s] = (int)pl->items.size();
+    for (int k = 0; k < rp; ++k) {
+      row_slot.push_back((unsigned char)cur.nslots);
+      row_coef.push_back(k < ncomp ? pl->grp_coef0[g] + k : -1);
+    }
+    cur.nrows += rp;
+    cur.nslots += 1;
+    rows += rp;
+    pl->n_a_nz += (long long)ncomp * pl->nf;
+  }
+  close_item();
+  pl->slot_row0[ns] = (int)rows;
+  pl->rows_total = rows;
+  pl->a_floats = rows * (long long)pl->nfp;
+  if (rows > INT_MAX / 4) {
+    delete pl;
+    return fail(CALB2_ERR_UNSUPPORTED, "too many basis rows (%lld)", rows);
+  }
+
+  // ---- coefficient -> row maps, antenna CSR ----
+  std::vector<int> coef_row0(nc), coef_grp(nc);
+  for (int g = 0; g < d->ngroups; ++g)
+    for (int k = 0; k < pl->grp_ncomp[g]; ++k) {
+      coef_row0[pl->grp_coef0[g] + k] = pl->slot_row0[pl->grp_slot0[g]] + k;
+      coef_grp[pl->grp_coef0[g] + k] = g;
+    }
+  std::vector<int> ant_ptr(d->nants + 1, 0), ant_ent(2 * nb);
+  for (long long b = 0; b < nb; ++b) {
+    ant_ptr[pl->bl_ant0[b] + 1]++;
+    ant_ptr[pl->bl_ant1[b] + 1]++;
+  }
+  for (int a = 0; a < d->nants; ++a) ant_ptr[a + 1] += ant_ptr[a];
+  {
+    std::vector<int> fill(ant_ptr.begin(), ant_ptr.end() - 1);
+    for (long long b = 0; b < nb; ++b) {  // ascending baseline order inside every antenna's list
+      ant_ent[fill[pl->bl_ant0[b]]++] = (int)(b << 1);
+      ant_ent[fill[pl->bl_ant1[b]]++] = (int)(b << 1) | 1;
+    }
+  }
+
+  std::vector<SlotGeom> geom(ns);
+  for (long long s = 0; s < ns; ++s) {
+    const ItemDesc& item = pl->items[pl->slot_item[s]];
+    geom[s].a_off = item.a_off;
+    geom[s].item_rows = item.nrows;
+    geom[s].row_in_item = pl->slot_row0[s] - item.row0;
+    geom[s].nbls = pl->slot_nbls[s];
+  }
+
+  // ---- device allocations ----
+  int rc = 0;
+#define TRY(x)          \
+  if (!rc) rc = (x);
+  CU(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  TRY(dalloc(pl->A, (size_t)pl->a_floats, pl));
+  TRY(upload(pl->d_items, pl->items, pl));
+  TRY(upload(pl->row_slot, row_slot, pl));
+  TRY(upload(pl->row_coef, row_coef, pl));
+  TRY(upload(pl->d_slot_row0, pl->slot_row0, pl));
+  TRY(upload(pl->d_slot_bl0, pl->slot_bl0, pl));
+  TRY(upload(pl->d_bl_ant0, pl->bl_ant0, pl));
+  TRY(upload(pl->d_bl_ant1, pl->bl_ant1, pl));
+  TRY(upload(pl->d_bl_slot, pl->bl_slot, pl));
+  TRY(upload(pl->ant_ptr, ant_ptr, pl));
+  TRY(upload(pl->ant_ent, ant_ent, pl));
+  TRY(upload(pl->coef_row0, coef_row0, pl));
+  TRY(upload(pl->coef_grp, coef_grp, pl));
+  TRY(upload(pl->d_grp_nslots, pl->grp_nslots, pl));
+  TRY(upload(pl->d_grp_slot0, pl->grp_slot0, pl));
+  TRY(upload(pl->d_grp_coef0, pl->grp_coef0, pl));
+  TRY(upload(pl->d_grp_ncomp, pl->grp_ncomp, pl));
+  TRY(upload(pl->slot_geom, geom, pl));
+  const size_t nd = (size_t)nb * pl->nfp, ng = (size_t)d->nants * pl->nfp;
+  TRY(dalloc(pl->d_r, nd, pl));
+  TRY(dalloc(pl->d_i, nd, pl));
+  TRY(dalloc(pl->w, nd, pl));
+  TRY(dalloc(pl->z, nd, pl));
+  for (int b = 0; b < 2; ++b) {
+    TRY(dalloc(pl->g_r[b], ng, pl));
+    TRY(dalloc(pl->g_i[b], ng, pl));
+  }
+  TRY(dalloc(pl->gm_r, ng, pl));
+  TRY(dalloc(pl->gu_r, ng, pl));
+  TRY(dalloc(pl->gm_i, ng, pl));
+  TRY(dalloc(pl->gu_i, ng, pl));
+  TRY(dalloc(pl->c_r, (size_t)nc, pl));
+  TRY(dalloc(pl->c_i, (size_t)nc, pl));
+  TRY(dalloc(pl->cm_r, (size_t)nc, pl));
+  TRY(dalloc(pl->cu_r, (size_t)nc, pl));
+  TRY(dalloc(pl->cm_i, (size_t)nc, pl));
+  TRY(dalloc(pl->cu_i, (size_t)nc, pl));
+  TRY(dalloc(pl->dcpart, (size_t)rows * 4, pl));
+  TRY(dalloc(pl->partials, pl->items.size() * 4, pl));
+  TRY(dalloc(pl->red_d, 4096, pl));
+  TRY(dalloc(pl->state, 1, pl));
+  TRY(dalloc(pl->state_eval, 1, pl));
+  TRY(dalloc(pl->comm_scalars, 4, pl));
+  pl->staging_floats = (size_t)64 << 20;  // 256 MiB of floats staged per batch
+  pl->staging_floats = std::max(pl->staging_floats, (size_t)pl->nf * 512);
+  TRY(dalloc(pl->staging, pl->staging_floats, pl, false));
+#undef TRY
+  if (!rc && cudaMallocHost(&pl->h_staging, pl->staging_floats * sizeof(float)) != cudaSuccess)
+    rc = fail(CALB2_ERR_CUDA, "cudaMallocHost(staging) failed");
+  if (!rc && cudaMallocHost(&pl->h_state, sizeof(FitState)) != cudaSuccess)
+    rc = fail(CALB2_ERR_CUDA, "cudaMallocHost(state) failed");
+  if (rc) {
+    calb2_plan_destroy(pl);
+    return rc;
+  }
+  *out = pl;
+  return 0;
+}
+
+int calb2_plan_destroy(calb2_plan* pl) {
+  if (!pl) return 0;
+  cudaSetDevice(pl->device);
+  if (pl->stream) cudaStreamSynchronize(pl->stream);
+  if (pl->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pl->comm);
+  DevBuf<float>* fb[] = {&pl->A, &pl->d_r, &pl->d_i, &pl->w, &pl->g_r[0], &pl->g_r[1], &pl->g_i[0], &pl->g_i[1],
+                         &pl->gm_r, &pl->gu_r, &pl->gm_i, &pl->gu_i, &pl->gsnap_r, &pl->gsnap_i, &pl->ggrad_r,
+                         &pl->ggrad_i, &pl->c_r, &pl->c_i, &pl->cm_r, &pl->cu_r, &pl->cm_i, &pl->cu_i, &pl->csnap_r,
+                         &pl->csnap_i, &pl->cgrad_r, &pl->cgrad_i, &pl->dcpart, &pl->hist, &pl->scratch_f, &pl->staging};
+  if (pl->nranks > 1) pl->ggrad_i.p = nullptr;  // a view into ggrad_r
+  for (auto* b : fb) b->release();
+  pl->z.release();
+  pl->y.release();
+  pl->vout.release();
+  pl->partials.release();
+  pl->red_d.release();
+  pl->comm_scalars.release();
+  pl->d_items.release();
+  pl->row_slot.release();
+  DevBuf<int>* ib[] = {&pl->row_coef, &pl->d_slot_row0, &pl->d_slot_bl0, &pl->d_bl_ant0, &pl->d_bl_ant1, &pl->d_bl_slot,
+                       &pl->ant_ptr, &pl->ant_ent, &pl->coef_row0, &pl->coef_grp, &pl->d_grp_nslots, &pl->d_grp_slot0,
+                       &pl->d_grp_coef0, &pl->d_grp_ncomp};
+  for (auto* b : ib) b->release();
+  pl->state.release();
+  pl->state_eval.release();
+  pl->slot_geom.release();
+  pl->sky_r.release();
+  pl->sky_i.release();
+  if (pl->h_staging) cudaFreeHost(pl->h_staging);
+  if (pl->h_state) cudaFreeHost(pl->h_state);
+  if (pl->stream) cudaStreamDestroy(pl->stream);
+  delete pl;
+  return 0;
+}
+
+int calb2_plan_get_info(const calb2_plan* pl, calb2_plan_info* info) {
+  if (!pl || !info) return fail(CALB2_ERR_ARG, "null argument");
+  info->n_d = pl->nbls * pl->nf;
+  info->n_a_nz = pl->n_a_nz;
+  info->n_a_stored = pl->a_floats;
+  info->n_c_nz = pl->ncoef;
+  info->nbls_total = pl->nbls;
+  info->nslots_total = pl->nslots;
+  info->nitems = (int64_t)pl->items.size();
+  info->tile_freqs = pl->FT;
+  info->rows_per_item_max = pl->KMAX;
+  info->device_bytes = (int64_t)pl->device_bytes;
+  return 0;
+}
+
+int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const float* const* blocks) {
+  if (!pl || !blocks) return fail(CALB2_ERR_ARG, "null argument");
+  if (g0 < 0 || ng < 0 || g0 + ng > pl->ngroups) return fail(CALB2_ERR_ARG, "group range out of bounds");
+  CU(cudaSetDevice(pl->device));
+  std::vector<RetileJob> jobs;
+  std::unordered_map<const float*, long long> seen;
+  size_t used = 0;
+  DevBuf<RetileJob> djobs;
+  auto flush = [&]() -> int {
+    if (jobs.empty()) return 0;
+    CU(cudaMemcpyAsync(pl->staging.p, pl->h_staging, used * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+    if (djobs.n < jobs.size()) CU(djobs.alloc(jobs.size() * 2));
+    CU(cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(RetileJob), cudaMemcpyHostToDevice, pl->stream));
+    retile_kernel<<<(unsigned)jobs.size(), 256, 0, pl->stream>>>(pl->staging.p, pl->A.p, djobs.p, pl->nf, pl->FT);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(pl->stream));
+    jobs.clear();
+    seen.clear();
+    used = 0;
+    return 0;
+  };
+  for (int gi = 0; gi < ng; ++gi) {
+    const int g = g0 + gi;
+    const float* blk = blocks[gi];
+    const int ncomp = pl->grp_ncomp[g], nsl = pl->grp_nslots[g];
+    const size_t need = (size_t)ncomp * nsl * pl->nf;
+    if (need == 0) continue;
+    if (!blk) return fail(CALB2_ERR_ARG, "group %d: null basis block", g);
+    if (need > pl->staging_floats) return fail(CALB2_ERR_UNSUPPORTED, "group %d basis block exceeds the staging buffer", g);
+    long long base;
+    auto it = seen.find(blk);
+    if (it != seen.end()) {
+      base = it->second;
+    } else {
+      if (used + need > pl->staging_floats)
+        if (int r = flush()) return r;
+      memcpy(pl->h_staging + used, blk, need * sizeof(float));
+      base = (long long)used;
+      seen.emplace(blk, base);
+      used += need;
+    }
+    for (int s = 0; s < nsl; ++s) {
+      const int slot = pl->grp_slot0[g] + s;
+      const ItemDesc& item = pl->items[pl->slot_item[slot]];
+      RetileJob jb{};
+      jb.src_off = base + (long long)s * ncomp * pl->nf;
+      jb.dst_off = item.a_off;
+      jb.ncomp = ncomp;
+      jb.item_rows = item.nrows;
+      jb.row_in_item = pl->slot_row0[slot] - item.row0;
+      jobs.push_back(jb);
+    }
+  }
+  if (int r = flush()) return r;
+  djobs.release();
+  pl->basis_groups_set += ng;
+  return 0;
+}
+
+int calb2_set_integration(calb2_plan* pl, const float* data_r, const float* data_i, const float* wgts) {
+  if (!pl || !data_r || !data_i || !wgts) return fail(CALB2_ERR_ARG, "null argument");
+  CU(cudaSetDevice(pl->device));
+  if (int r = upload_padded(pl, data_r, pl->d_r.p, (size_t)pl->nbls, 0.f)) return r;
+  if (int r = upload_padded(pl, data_i, pl->d_i.p, (size_t)pl->nbls, 0.f)) return r;
+  if (int r = upload_padded(pl, wgts, pl->w.p, (size_t)pl->nbls, 0.f)) return r;
+  pl->have_data = true;
+  return 0;
+}
+
+int calb2_set_gains(calb2_plan* pl, const float* g_r, const float* g_i) {
+  if (!pl || !g_r || !g_i) return fail(CALB2_ERR_ARG, "null argument");
+  CU(cudaSetDevice(pl->device));
+  pl->cur_buf = 0;
+  if (int r = upload_padded(pl, g_r, pl->g_r[0].p, (size_t)pl->nants, 1.f)) return r;
+  if (int r = upload_padded(pl, g_i, pl->g_i[0].p, (size_t)pl->nants, 0.f)) return r;
+  pl->have_gains = true;
+  return 0;
+}
+
+int calb2_set_coeffs(calb2_plan* pl, const float* coef_r, const float* coef_i) {
+  if (!pl || !coef_r || !coef_i) return fail(CALB2_ERR_ARG, "null argument");
+  CU(cudaSetDevice(pl->device));
+  CU(cudaMemcpy(pl->c_r.p, coef_r, pl->ncoef * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->c_i.p, coef_i, pl->ncoef * sizeof(float), cudaMemcpyHostToDevice));
+  pl->have_coeffs = true;
+  return 0;
+}
+
+int calb2_get_gains(calb2_plan* pl, float* g_r, float* g_i) {
+  if (!pl || !g_r || !g_i) return fail(CALB2_ERR_ARG, "null argument");
+  CU(cudaSetDevice(pl->device));
+  if (int r = download_unpadded(pl, pl->g_r[pl->cur_buf].p, g_r, (size_t)pl->nants)) return r;
+  return download_unpadded(pl, pl->g_i[pl->cur_buf].p, g_i, (size_t)pl->nants);
+}
+
+int calb2_get_coeffs(calb2_plan* pl, float* coef_r, float* coef_i) {
+  if (!pl || !coef_r || !coef_i) return fail(CALB2_ERR_ARG, "null argument");
+  CU(cudaSetDevice(pl->device));
+  CU(cudaStreamSynchronize(pl->stream));
+  CU(cudaMemcpy(coef_r, pl->c_r.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(coef_i, pl->c_i.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int calb2_get_weights(calb2_plan* pl, float* wgts) {
+  if (!pl || !wgts) return fail(CALB2_ERR_ARG, "null argument");
+  CU(cudaSetDevice(pl->device));
+  return download_unpadded(pl, pl->w.p, wgts, (size_t)pl->nbls);
+}
+
+static int run_forward_store_v(calb2_plan* pl) {
+  if (int r = ensure_vout(pl)) return r;
+  if (int r = set_eval_state(pl)) return r;
+  HeavyParams hp = heavy_params(pl, pl->state_eval.p, false, 1, 0);
+  CU(launch_heavy(pl->FL, false, hp, (int)pl->items.size(), pl->stream));
+  return 0;
+}
+
+int calb2_get_model(calb2_plan* pl, float* model_r, float* model_i) {
+  if (!pl || !model_r || !model_i) return fail(CALB2_ERR_ARG, "null argument");
+  if (!pl->have_data || !pl->have_gains || !pl->have_coeffs) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
+  CU(cudaSetDevice(pl->device));
+  if (int r = run_forward_store_v(pl)) return r;
+  // gather per baseline through the staging buffer: real rows then imaginary rows
+  const size_t rows_per = std::max<size_t>(1, pl->staging_floats / ((size_t)2 * pl->nf));
+  for (size_t b0 = 0; b0 < (size_t)pl->nbls; b0 += rows_per) {
+    const size_t n = std::min(rows_per, (size_t)pl->nbls - b0);
+    float* sr = pl->staging.p;
+    float* si = pl->staging.p + n * pl->nf;
+    model_gather_kernel<<<(unsigned)n, 128, 0, pl->stream>>>(pl->vout.p, pl->d_bl_slot.p + b0, sr, si, pl->nf, pl->nfp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pl->h_staging, pl->staging.p, 2 * n * pl->nf * sizeof(float), cudaMemcpyDeviceToHost, pl->stream));
+    CU(cudaStreamSynchronize(pl->stream));
+    memcpy(model_r + b0 * pl->nf, pl->h_staging, n * pl->nf * sizeof(float));
+    memcpy(model_i + b0 * pl->nf, pl->h_staging + n * pl->nf, n * pl->nf * sizeof(float));
+  }
+  return 0;
+}
+
+static int device_sum(calb2_plan* pl, const float* x, const float* y, size_t n, double* out) {
+  const int nb = 1024;
+  dot_partial_kernel<<<nb, 256, 0, pl->stream>>>(x, y, n, pl->red_d.p);
+  CU(cudaGetLastError());
+  std::vector<double> h(nb);
+  CU(cudaMemcpyAsync(h.data(), pl->red_d.p, nb * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+  CU(cudaStreamSynchronize(pl->stream));
+  double t = 0.0;
+  for (double v : h) t += v;
+  *out = t;
+  return 0;
+}
+
+int calb2_prior_sums(calb2_plan* pl, const float* sky_r, const float* sky_i, float* prior_r, float* prior_i) {
+  if (!pl || !sky_r || !sky_i || !prior_r || !prior_i) return fail(CALB2_ERR_ARG, "null argument");
+  if (!pl->have_data) return fail(CALB2_ERR_STATE, "set_integration first (weights)");
+  CU(cudaSetDevice(pl->device));
+  const size_t nd = (size_t)pl->nbls * pl->nfp;
+  if (pl->scratch_f.n < nd)
+    if (int r = dalloc(pl->scratch_f, nd, pl)) return r;
+  double t = 0.0;
+  if (int r = upload_padded(pl, sky_r, pl->scratch_f.p, (size_t)pl->nbls, 0.f)) return r;
+  if (int r = device_sum(pl, pl->scratch_f.p, pl->w.p, nd, &t)) return r;
+  *prior_r = (float)t;
+  if (int r = upload_padded(pl, sky_i, pl->scratch_f.p, (size_t)pl->nbls, 0.f)) return r;
+  if (int r = device_sum(pl, pl->scratch_f.p, pl->w.p, nd, &t)) return r;
+  *prior_i = (float)t;
+  return 0;
+}
+
+int calb2_apply_model_snr_weights(calb2_plan* pl) {
+  if (!pl) return fail(CALB2_ERR_ARG, "null argument");
+  if (!pl->have_data || !pl->have_coeffs || !pl->have_gains) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
+  CU(cudaSetDevice(pl->device));
+  if (int r = run_forward_store_v(pl)) return r;
+  snr_weight_kernel<<<(unsigned)pl->nbls, 128, 0, pl->stream>>>(pl->w.p, pl->vout.p, pl->d_bl_slot.p, pl->nfp, 1.f);
+  CU(cudaGetLastError());
+  double t = 0.0;
+  const size_t nd = (size_t)pl->nbls * pl->nfp;
+  if (int r = device_sum(pl, pl->w.p, nullptr, nd, &t)) return r;
+  scale_kernel<<<1024, 256, 0, pl->stream>>>(pl->w.p, nd, (float)t);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(pl->stream));
+  return 0;
+}
+
+int calb2_init_coeffs(calb2_plan* pl, const float* sky_r, const float* sky_i) {
+  if (!pl || !sky_r || !sky_i) return fail(CALB2_ERR_ARG, "null argument");
+  if (!pl->have_data) return fail(CALB2_ERR_STATE, "set_integration first (weights)");
+  CU(cudaSetDevice(pl->device));
+  return init_coeffs_impl(pl, sky_r, sky_i);
+}
+
+int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, float prior_i, float* loss, float* dg_r,
+                         float* dg_i, float* dc_r, float* dc_i) {
+  if (!pl) return fail(CALB2_ERR_ARG, "null argument");
+  if (!pl->have_data || !pl->have_gains || !pl->have_coeffs) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
+  CU(cudaSetDevice(pl->device));
+  const bool sum = regularization == CALB2_REG_SUM;
+  if (sum)
+    if (int r = ensure_sum_buffers(pl)) return r;
+  if (int r = ensure_grad_buffers(pl)) return r;
+  if (int r = set_eval_state(pl)) return r;
+  FitConsts k{};
+  k.regularization = regularization;
+  k.prior_r = prior_r;
+  k.prior_i = prior_i;
+  HeavyParams hp = heavy_params(pl, pl->state_eval.p, sum, 0, 0);
+  CU(launch_heavy(pl->FL, sum, hp, (int)pl->items.size(), pl->stream));
+  FinalizeParams fp{};
+  fp.partials = pl->partials.p;
+  fp.nitems = (int)pl->items.size();
+  fp.st = pl->state_eval.p;
+  fp.k = k;
+  fp.eval_only = 1;
+  finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
+  CU(cudaGetLastError());
+  dim3 ggrid((pl->nfp + 127) / 128, pl->nants);
+  gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state_eval.p, k, 1, sum, 1));
+  CU(cudaGetLastError());
+  coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(coeff_params(pl, pl->state_eval.p, k, 1, sum));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(pl->h_state, pl->state_eval.p, sizeof(FitState), cudaMemcpyDeviceToHost, pl->stream));
+  CU(cudaStreamSynchronize(pl->stream));
+  if (loss) *loss = pl->h_state->last_loss;
+  if (dg_r)
+    if (int r = download_unpadded(pl, pl->ggrad_r.p, dg_r, (size_t)pl->nants)) return r;
+  if (dg_i)
+    if (int r = download_unpadded(pl, pl->ggrad_i.p, dg_i, (size_t)pl->nants)) return r;
+  if (dc_r) CU(cudaMemcpy(dc_r, pl->cgrad_r.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToHost));
+  if (dc_i) CU(cudaMemcpy(dc_i, pl->cgrad_i.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, calb2_fit_result* res) {
+  if (!pl || !o || !res) return fail(CALB2_ERR_ARG, "null argument");
+  if (!pl->have_data || !pl->have_gains || !pl->have_coeffs) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
+  if (o->optimizer < 0 || o->optimizer > 2) return fail(CALB2_ERR_ARG, "unknown optimizer id %d", o->optimizer);
+  if (o->maxsteps < 0 || o->n_profile_steps < 0) return fail(CALB2_ERR_ARG, "negative step count");
+  if (o->maxsteps > 0 && !loss_history) return fail(CALB2_ERR_ARG, "loss_history is null");
+  CU(cudaSetDevice(pl->device));
+  const bool sum = o->regularization == CALB2_REG_SUM;
+  const bool freeze = o->freeze_model != 0;
+  if (sum)
+    if (int r = ensure_sum_buffers(pl)) return r;
+  if (o->use_min)
+    if (int r = ensure_use_min_buffers(pl)) return r;
+  if (pl->nranks > 1)
+    if (int r = ensure_grad_buffers(pl)) return r;
+  FitConsts k{};
+  k.optimizer = o->optimizer;
+  k.lr = o->learning_rate;
+  k.beta1 = o->beta_1;
+  k.beta2 = o->beta_2;
+  k.eps = o->epsilon;
+  k.maxsteps = o->maxsteps;
+  k.tol = o->tol;
+  k.use_min = o->use_min;
+  k.regularization = o->regularization;
+  k.prior_r = o->prior_r_sum;
+  k.prior_i = o->prior_i_sum;
+  k.n_skip = o->n_profile_steps + 1;
+  const long long total = (long long)k.n_skip + o->maxsteps;
+
+  // gains must start in buffer 0 (the step parity selects the buffer)
+  const size_t ng = (size_t)pl->nants * pl->nfp;
+  if (pl->cur_buf == 1) {
+    CU(cudaMemcpyAsync(pl->g_r[0].p, pl->g_r[1].p, ng * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+    CU(cudaMemcpyAsync(pl->g_i[0].p, pl->g_i[1].p, ng * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+    pl->cur_buf = 0;
+  }
+  // fresh optimizer per integration (calibration.py:571): zero slots and step counter
+  DevBuf<float>* slots[] = {&pl->gm_r, &pl->gu_r, &pl->gm_i, &pl->gu_i, &pl->cm_r, &pl->cu_r, &pl->cm_i, &pl->cu_i};
+  for (auto* s : slots) CU(cudaMemsetAsync(s->p, 0, s->bytes(), pl->stream));
+  if (pl->hist.n < (size_t)std::max(1, o->maxsteps)) {
+    if (int r = dalloc(pl->hist, (size_t)std::max(1, o->maxsteps), pl)) return r;
+  }
+  FitState s0{};
+  s0.step = 0;
+  s0.stop_after = (int)(total - 1);
+  s0.min_loss = INFINITY;
+  CU(cudaMemcpyAsync(pl->state.p, &s0, sizeof(s0), cudaMemcpyHostToDevice, pl->stream));
+
+  int chunk = o->steps_per_sync > 0 ? o->steps_per_sync : 32;
+  const bool time_heavy = !o->use_graph;
+  std::vector<cudaEvent_t> evs;
+  cudaEvent_t ev_begin, ev_end;
+  CU(cudaEventCreate(&ev_begin));
+  CU(cudaEventCreate(&ev_end));
+  if (time_heavy) {
+    evs.resize(2 * chunk);
+    for (auto& e : evs) CU(cudaEventCreate(&e));
+  }
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  long long launches = 0, heavy_launches = 0;
+  double heavy_ms = 0.0;
+  int rc = 0;
+  if (o->use_graph && pl->nranks == 1) {
+    long long dummy = 0;
+    CU(cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < chunk && !rc; ++i) rc = enqueue_step(pl, k, sum, freeze, pl->hist.p, nullptr, nullptr, &dummy);
+    cudaError_t ce = cudaStreamEndCapture(pl->stream, &graph);
+    if (rc) return rc;
+    CU(ce);
+    CU(cudaGraphInstantiate(&gexec, graph, 0));
+  }
+  CU(cudaEventRecord(ev_begin, pl->stream));
+  long long done = 0;
+  while (done < total) {
+    const int n = (int)std::min<long long>(chunk, total - done);
+    if (gexec) {
+      CU(cudaGraphLaunch(gexec, pl->stream));
+      launches += (long long)chunk * (freeze && !k.use_min ? 3 : 4);
+      heavy_launches += chunk;
+    } else {
+      for (int i = 0; i < n; ++i) {
+        if (int r = enqueue_step(pl, k, sum, freeze, pl->hist.p, time_heavy ? evs[2 * i] : nullptr,
+                                 time_heavy ? evs[2 * i + 1] : nullptr, &launches))
+          return r;
+        heavy_launches++;
+      }
+    }
+    done += gexec ? chunk : n;
+    CU(cudaMemcpyAsync(pl->h_state, pl->state.p, sizeof(FitState), cudaMemcpyDeviceToHost, pl->stream));
+    CU(cudaStreamSynchronize(pl->stream));
+    const bool stopped = pl->h_state->step > pl->h_state->stop_after;
+    if (time_heavy) {
+        for (int i = 0; i < n; ++i) {  // kernels past the stop are no-ops with ~zero duration
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, evs[2 * i], evs[2 * i + 1]));
+        heavy_ms += ms;
+      }
+    }
+    if (stopped) break;
+  }
+  CU(cudaEventRecord(ev_end, pl->stream));
+  CU(cudaStreamSynchronize(pl->stream));
+  float loop_ms = 0.f;
+  CU(cudaEventElapsedTime(&loop_ms, ev_begin, ev_end));
+  const FitState hs = *pl->h_state;
+  pl->cur_buf = hs.step & 1;
+
+  // calibration.py:702-710 / 722-732: pick the optimum
+  if (o->use_min) {
+    if (hs.any_snap) {
+      CU(cudaMemcpyAsync(pl->g_r[pl->cur_buf].p, pl->gsnap_r.p, ng * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+      CU(cudaMemcpyAsync(pl->g_i[pl->cur_buf].p, pl->gsnap_i.p, ng * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+      if (!freeze) {
+        CU(cudaMemcpyAsync(pl->c_r.p, pl->csnap_r.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+        CU(cudaMemcpyAsync(pl->c_i.p, pl->csnap_i.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+      }
+    }
+  }
+  if (hs.nrec > 0 && loss_history)
+    CU(cudaMemcpyAsync(loss_history, pl->hist.p, hs.nrec * sizeof(float), cudaMemcpyDeviceToHost, pl->stream));
+  CU(cudaStreamSynchronize(pl->stream));
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  for (auto& e : evs) cudaEventDestroy(e);
+  cudaEventDestroy(ev_begin);
+  cudaEventDestroy(ev_end);
+
+  res->nsteps_recorded = hs.nrec;
+  res->nsteps_total = hs.step;
+  res->final_loss = o->use_min ? hs.min_loss : hs.last_loss;
+  res->loop_ms = loop_ms;
+  res->heavy_ms = (float)heavy_ms;
+  res->heavy_launches = time_heavy ? (int64_t)hs.step : heavy_launches;
+  res->kernel_launches = launches;
+  if (!std::isfinite(hs.last_loss)) g_err = "loss is not finite";
+  return 0;
+}
+
+int calb2_comm_unique_id(void* id_out, const char* nccl_lib) {
+  if (!id_out) return fail(CALB2_ERR_ARG, "null argument");
+  if (int r = load_nccl(nccl_lib)) return r;
+  int rc = g_nccl.GetUniqueId(id_out);
+  if (rc != 0) return fail(CALB2_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  return 0;
+}
+
+int calb2_comm_init(calb2_plan* pl, const void* id, int32_t rank, int32_t nranks, const char* nccl_lib) {
+  if (!pl || !id) return fail(CALB2_ERR_ARG, "null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(CALB2_ERR_ARG, "bad rank/nranks");
+  if (nranks == 1) return 0;
+  if (int r = load_nccl(nccl_lib)) return r;
+  CU(cudaSetDevice(pl->device));
+  IdBlob blob;
+  memcpy(blob.bytes, id, sizeof(blob.bytes));
+  int rc = g_nccl.CommInitRank(&pl->comm, nranks, blob, rank);
+  if (rc != 0) return fail(CALB2_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  pl->rank = rank;
+  pl->nranks = nranks;
+  // the gain-gradient tables are all-reduced in one call: make them one allocation
+  pl->ggrad_r.release();
+  pl->ggrad_i.release();
+  const size_t ng = (size_t)pl->nants * pl->nfp;
+  CU(pl->ggrad_r.alloc(2 * ng));
+  CU(cudaMemset(pl->ggrad_r.p, 0, 2 * ng * sizeof(float)));
+  pl->ggrad_i.p = pl->ggrad_r.p + ng;  // view; never released separately
+  pl->ggrad_i.n = 0;
+  return 0;
+}
+
+}  // extern "C"

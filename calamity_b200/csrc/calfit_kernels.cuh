@@ -1,0 +1,772 @@
+// Device code of the B200-native gain-and-foreground fit (sm_100a).
+//
+// One optimizer iteration of calibration.py:663-668 is four launches on one stream:
+//   heavy_kernel   streams the ragged foreground basis ONCE (cp.async.bulk -> shared memory, mbarrier
+//                  double buffering) and, per staged [rows x FT channels] tile, does the forward
+//                  contraction v = sum_k c_k A_k (calibration.py:1587-1590), the gain application,
+//                  weighted residual and chi^2 partial sums (1593-1609 / 1643-1651), dL/dv, and the
+//                  backward contraction A . dL/dv accumulated in registers across the item's tiles.
+//   finalize_kernel reduces the per-CTA partial sums in a fixed order (deterministic), forms the loss
+//                  (1652-1656), records it, runs the use_min / tol logic of 699-717 on the device.
+//   gains_kernel   deterministic per-(antenna, channel) reduction of the gain gradient over the
+//                  baselines touching the antenna (CSR order, no atomics) + optimizer step on the gains.
+//   coeffs_kernel  optimizer step on the foreground coefficients (combines the regulariser terms).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace calb2 {
+
+// ------------------------------------------------------------------------------------------------
+// shared host/device structures
+// ------------------------------------------------------------------------------------------------
+struct ItemDesc {
+  long long a_off;  // float offset of the item's first tile in the tiled basis
+  int nrows;        // staged rows (multiple of the warp-step G), <= KMAX
+  int nslots;       // model-visibility slots in the item, <= SMAX
+  int row0;         // global (padded) row index of the item's first row
+  int slot0;        // global slot index of the item's first slot
+};
+
+struct FitState {
+  int step;          // train steps executed so far (0-based index of the step in flight)
+  int stop_after;    // last step allowed to execute
+  int nrec;          // recorded losses
+  int upd_active;    // set by finalize when this step's updates must run
+  int snap;          // use_min: this step's post-update parameters are the new optimum
+  int any_snap;
+  float min_loss;
+  float prev_loss;
+  float last_loss;
+  float alpha;       // 2 (S_r - P_r)   (d/dS of the 'sum' regulariser, calibration.py:1654)
+  float beta;        // 2 (S_i - P_i)
+  float lr_t;        // bias-corrected step size of the update in flight
+  float s_r, s_i;
+  double chi2;
+};
+
+struct FitConsts {
+  int optimizer;
+  float lr, beta1, beta2, eps;
+  int maxsteps;
+  double tol;
+  int use_min;
+  int regularization;
+  float prior_r, prior_i;
+  int n_skip;        // n_profile_steps + 1 unrecorded steps
+};
+
+struct HeavyParams {
+  const float* A;
+  const ItemDesc* items;
+  const unsigned char* row_slot;  // [rows_total] slot index local to the item
+  const int* row_coef;            // [rows_total] coefficient index, -1 for alignment rows
+  const int* slot_row0;           // [nslots_total + 1] global row of each slot's first row
+  const int* slot_bl0;            // [nslots_total + 1] first baseline of each slot
+  const int* bl_ant0;
+  const int* bl_ant1;
+  const float* d_r;               // [nbls][nfp]
+  const float* d_i;
+  const float* w;
+  const float* g_r[2];            // ping-pong gains [nants][nfp]
+  const float* g_i[2];
+  const float* c_r;               // [ncoef]
+  const float* c_i;
+  float2* z;                      // [nbls][nfp]  (a, b) of the gain gradient, chi^2 part
+  float2* y;                      // [nbls][nfp]  w * v (regulariser part), only when SUM
+  float* dcpart;                  // [rows_total][NQ] backward contractions per staged row
+  float2* vout;                   // [nslots_total][nfp] model visibilities, written when store_v
+  double* partials;               // [nitems][4]: chi^2, S_r, S_i
+  const FitState* st;
+  int nfp;                        // channels padded to a multiple of FT
+  int ntiles;
+  int store_v;
+  int init_mode;                  // 1: dL/dv := data * (w != 0)   (right-hand side of the lstsq initialisation)
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk asynchronous copy (TMA engine, SASS UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+__device__ __forceinline__ void axpy4(float c, const float4& a, float4& v) {
+  v.x = fmaf(c, a.x, v.x);
+  v.y = fmaf(c, a.y, v.y);
+  v.z = fmaf(c, a.z, v.z);
+  v.w = fmaf(c, a.w, v.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// heavy kernel configuration
+//   FL   lanes along frequency (a lane owns a float4 of channels)  -> FT = 4 FL channels per tile
+//   G    rows a warp reads per step (32 / FL): G consecutive rows are G*FT*4 contiguous bytes, so every
+//        warp-wide LDS.128 touches one contiguous 512-byte span (bank-conflict free)
+//   RPT  steps per warp; KMAX = 8 warps * RPT * G rows per item
+// ------------------------------------------------------------------------------------------------
+template <int FL_, bool SUM_, int RPT_>
+struct HeavyCfg {
+  static constexpr int FL = FL_;
+  static constexpr bool SUM = SUM_;
+  static constexpr int RPT = RPT_;
+  static constexpr int NTHR = 256;
+  static constexpr int NWARP = 8;
+  static constexpr int G = 32 / FL;
+  static constexpr int FT = FL * 4;
+  static constexpr int NSTEP = NWARP * RPT;
+  static constexpr int KMAX = NSTEP * G;
+  static constexpr int TILE_FLOATS = KMAX * FT;
+  static constexpr int SMAX = 8;
+  static constexpr int NQ = SUM ? 4 : 2;
+  static constexpr int NSEG = NWARP + SMAX;
+  static constexpr int NBUF = 2;
+  // shared memory carve-up (bytes)
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_VPART = OFF_A + NBUF * TILE_FLOATS * 4;
+  static constexpr int OFF_QBUF = OFF_VPART + NSEG * 2 * FT * 4;
+  static constexpr int OFF_CBUF = OFF_QBUF + SMAX * NQ * FT * 4;
+  static constexpr int OFF_STEPSLOT = OFF_CBUF + KMAX * 8;
+  static constexpr int OFF_SLOTSTEP0 = OFF_STEPSLOT + ((NSTEP + 15) / 16) * 16;
+  static constexpr int OFF_SLOTBL0 = OFF_SLOTSTEP0 + (SMAX + 1) * 4 + 12;
+  static constexpr int OFF_RED = OFF_SLOTBL0 + (SMAX + 1) * 4 + 12;
+  static constexpr int OFF_MBAR = OFF_RED + NWARP * 4 * 4;
+  static constexpr int SMEM_BYTES = OFF_MBAR + NBUF * 8;
+};
+
+template <int FL, bool SUM, int RPT>
+__global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
+  using C = HeavyCfg<FL, SUM, RPT>;
+  constexpr int G = C::G, FT = C::FT, NQ = C::NQ;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const FitState* st = p.st;
+  if (st->step > st->stop_after) return;  // fit already stopped (uniform across the grid)
+  const int gsel = st->step & 1;
+  const float* __restrict__ g_r = p.g_r[gsel];
+  const float* __restrict__ g_i = p.g_i[gsel];
+
+  float* Abuf = reinterpret_cast<float*>(smem + C::OFF_A);
+  float* vpart = reinterpret_cast<float*>(smem + C::OFF_VPART);
+  float* qbuf = reinterpret_cast<float*>(smem + C::OFF_QBUF);
+  float2* cbuf = reinterpret_cast<float2*>(smem + C::OFF_CBUF);
+  unsigned char* step_slot = smem + C::OFF_STEPSLOT;
+  int* slot_step0 = reinterpret_cast<int*>(smem + C::OFF_SLOTSTEP0);
+  int* slot_bl0 = reinterpret_cast<int*>(smem + C::OFF_SLOTBL0);
+  float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::OFF_MBAR);
+
+  const ItemDesc it = p.items[blockIdx.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int usub = lane / FL, fl = lane % FL;
+  const int nsteps = it.nrows / G;
+  const uint32_t tile_bytes = (uint32_t)it.nrows * FT * 4u;
+  const float* Abase = p.A + it.a_off;
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
+  for (int r = tid; r < it.nrows; r += C::NTHR) {
+    const int ci = p.row_coef[it.row0 + r];
+    cbuf[r] = (ci >= 0 && !p.init_mode) ? make_float2(p.c_r[ci], p.c_i[ci]) : make_float2(0.f, 0.f);
+  }
+  for (int s = tid; s < nsteps; s += C::NTHR) step_slot[s] = p.row_slot[it.row0 + s * G];
+  for (int s = tid; s <= it.nslots; s += C::NTHR) {
+    slot_step0[s] = (p.slot_row0[it.slot0 + s] - it.row0) / G;
+    slot_bl0[s] = p.slot_bl0[it.slot0 + s];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&mbar[0], tile_bytes);
+    bulk_g2s(Abuf, Abase, tile_bytes, &mbar[0]);
+  }
+
+  float acc[RPT][NQ];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[i][q] = 0.f;
+  float loss_acc = 0.f, sr_acc = 0.f, si_acc = 0.f;
+
+  for (int j = 0; j < p.ntiles; ++j) {
+    const int buf = j & 1;
+    if (tid == 0 && j + 1 < p.ntiles) {
+      mbar_expect_tx(&mbar[buf ^ 1], tile_bytes);
+      bulk_g2s(Abuf + (buf ^ 1) * C::TILE_FLOATS, Abase + (size_t)(j + 1) * it.nrows * FT, tile_bytes, &mbar[buf ^ 1]);
+    }
+    mbar_wait(&mbar[buf], (j >> 1) & 1);
+    const float* Ab = Abuf + buf * C::TILE_FLOATS;
+
+    // ---------------- phase F: forward contraction, partial per (warp, slot) ----------------
+    {
+      float4 vr = make_float4(0.f, 0.f, 0.f, 0.f), vi = vr;
+      int cur = -1;
+      auto flush = [&](int seg) {
+#pragma unroll
+        for (int off = FL; off < 32; off <<= 1) {
+          vr.x += __shfl_xor_sync(0xffffffffu, vr.x, off);
+          vr.y += __shfl_xor_sync(0xffffffffu, vr.y, off);
+          vr.z += __shfl_xor_sync(0xffffffffu, vr.z, off);
+          vr.w += __shfl_xor_sync(0xffffffffu, vr.w, off);
+          vi.x += __shfl_xor_sync(0xffffffffu, vi.x, off);
+          vi.y += __shfl_xor_sync(0xffffffffu, vi.y, off);
+          vi.z += __shfl_xor_sync(0xffffffffu, vi.z, off);
+          vi.w += __shfl_xor_sync(0xffffffffu, vi.w, off);
+        }
+        if (usub == 0) {
+          *reinterpret_cast<float4*>(vpart + (seg * 2 + 0) * FT + fl * 4) = vr;
+          *reinterpret_cast<float4*>(vpart + (seg * 2 + 1) * FT + fl * 4) = vi;
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int stp = warp * RPT + i;
+        if (stp < nsteps) {  // warp-uniform
+          const int s = step_slot[stp];
+          if (s != cur) {
+            if (cur >= 0) flush(warp + cur);
+            vr = make_float4(0.f, 0.f, 0.f, 0.f);
+            vi = vr;
+            cur = s;
+          }
+          const int r = stp * G + usub;
+          const float4 a = *reinterpret_cast<const float4*>(Ab + r * FT + fl * 4);
+          const float2 c = cbuf[r];
+          axpy4(c.x, a, vr);
+          axpy4(c.y, a, vi);
+        }
+      }
+      if (cur >= 0) flush(warp + cur);
+    }
+    __syncthreads();
+
+    // ---------------- phase Q: gains, model, residual, chi^2, dL/dv ----------------
+    for (int e = tid; e < it.nslots * FT; e += C::NTHR) {
+      const int s = e / FT, f = e % FT;
+      const int fg = j * FT + f;
+      const int w_lo = slot_step0[s] / RPT, w_hi = (slot_step0[s + 1] - 1) / RPT;
+      float v_r = 0.f, v_i = 0.f;
+      for (int w = w_lo; w <= w_hi; ++w) {
+        v_r += vpart[((w + s) * 2 + 0) * FT + f];
+        v_i += vpart[((w + s) * 2 + 1) * FT + f];
+      }
+      float qr = 0.f, qi = 0.f, pw = 0.f, qw = 0.f;
+      for (int b = slot_bl0[s]; b < slot_bl0[s + 1]; ++b) {
+        const size_t o = (size_t)b * p.nfp + fg;
+        const float dr = p.d_r[o], di = p.d_i[o], w = p.w[o];
+        if (p.init_mode) {  // right-hand side of the coefficient initialisation: data * (w != 0)
+          const float msk = (fabsf(w) <= 1e-8f) ? 0.f : 1.f;  // np.isclose(w, 0): |w| <= atol = 1e-8
+          qr += dr * msk;
+          qi += di * msk;
+          continue;
+        }
+        const size_t o0 = (size_t)p.bl_ant0[b] * p.nfp + fg, o1 = (size_t)p.bl_ant1[b] * p.nfp + fg;
+        const float gr0 = g_r[o0], gi0 = g_i[o0], gr1 = g_r[o1], gi1 = g_i[o1];
+        const float P = gr0 * gr1 + gi0 * gi1;
+        const float Q = gr0 * gi1 - gi0 * gr1;
+        const float mr = P * v_r + Q * v_i;
+        const float mi = P * v_i - Q * v_r;
+        const float rr = dr - mr, ri = di - mi;
+        loss_acc += (rr * rr + ri * ri) * w;
+        const float er = -2.f * w * rr, ei = -2.f * w * ri;
+        p.z[o] = make_float2(er * v_r + ei * v_i, er * v_i - ei * v_r);
+        qr += P * er - Q * ei;
+        qi += Q * er + P * ei;
+        if (SUM) {
+          p.y[o] = make_float2(w * v_r, w * v_i);
+          sr_acc += w * mr;
+          si_acc += w * mi;
+          pw += P * w;
+          qw += Q * w;
+        }
+      }
+      qbuf[(s * NQ + 0) * FT + f] = qr;
+      qbuf[(s * NQ + 1) * FT + f] = qi;
+      if (SUM) {
+        qbuf[(s * NQ + 2) * FT + f] = pw;
+        qbuf[(s * NQ + 3) * FT + f] = qw;
+      }
+      if (p.store_v) p.vout[(size_t)(it.slot0 + s) * p.nfp + fg] = make_float2(v_r, v_i);
+    }
+    __syncthreads();
+
+    // ---------------- phase B: backward contraction, accumulated in registers ----------------
+    {
+      float4 q0, q1, q2, q3;
+      int cur = -1;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int stp = warp * RPT + i;
+        if (stp < nsteps) {
+          const int s = step_slot[stp];
+          if (s != cur) {
+            q0 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 0) * FT + fl * 4);
+            q1 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 1) * FT + fl * 4);
+            if (SUM) {
+              q2 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 2) * FT + fl * 4);
+              q3 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 3) * FT + fl * 4);
+            }
+            cur = s;
+          }
+          const int r = stp * G + usub;
+          const float4 a = *reinterpret_cast<const float4*>(Ab + r * FT + fl * 4);
+          acc[i][0] = dot4(a, q0, acc[i][0]);
+          acc[i][1] = dot4(a, q1, acc[i][1]);
+          if (SUM) {
+            acc[i][2] = dot4(a, q2, acc[i][2]);
+            acc[i][3] = dot4(a, q3, acc[i][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // tile buffer, vpart and qbuf are free for the next tile
+  }
+
+  // ---------------- item epilogue: lane reduction of the backward sums ----------------
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float v = acc[i][q];
+#pragma unroll
+      for (int off = 1; off < FL; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      acc[i][q] = v;
+    }
+    const int stp = warp * RPT + i;
+    if (stp < nsteps && fl == 0) {
+      float* dst = p.dcpart + (size_t)(it.row0 + stp * G + usub) * NQ;
+      if (SUM)
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      else
+        *reinterpret_cast<float2*>(dst) = make_float2(acc[i][0], acc[i][1]);
+    }
+  }
+
+  // ---------------- per-CTA partial sums (fixed order -> deterministic) ----------------
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+    sr_acc += __shfl_xor_sync(0xffffffffu, sr_acc, off);
+    si_acc += __shfl_xor_sync(0xffffffffu, si_acc, off);
+  }
+  if (lane == 0) {
+    red[warp * 4 + 0] = loss_acc;
+    red[warp * 4 + 1] = sr_acc;
+    red[warp * 4 + 2] = si_acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int w = 0; w < C::NWARP; ++w) {
+      a += (double)red[w * 4 + 0];
+      b += (double)red[w * 4 + 1];
+      c += (double)red[w * 4 + 2];
+    }
+    double* dst = p.partials + (size_t)blockIdx.x * 4;
+    dst[0] = a;
+    dst[1] = b;
+    dst[2] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: deterministic reduction of the per-CTA partials + loop control (calibration.py:699-717)
+// ------------------------------------------------------------------------------------------------
+struct FinalizeParams {
+  const double* partials;
+  int nitems;
+  FitState* st;
+  FitConsts k;
+  float* hist;
+  int eval_only;  // 1: just publish loss / alpha / beta, no loop bookkeeping
+};
+
+__global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams p) {
+  __shared__ double sh[3][32];
+  FitState* st = p.st;
+  if (!p.eval_only && st->step > st->stop_after) {
+    if (threadIdx.x == 0) st->upd_active = 0;
+    return;
+  }
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < p.nitems; i += blockDim.x) {
+    a += p.partials[(size_t)i * 4 + 0];
+    b += p.partials[(size_t)i * 4 + 1];
+    c += p.partials[(size_t)i * 4 + 2];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+    c += __shfl_xor_sync(0xffffffffu, c, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sh[0][warp] = a;
+    sh[1][warp] = b;
+    sh[2][warp] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  a = b = c = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+    a += sh[0][w];
+    b += sh[1][w];
+    c += sh[2][w];
+  }
+  float loss = (float)a;
+  float alpha = 0.f, beta = 0.f;
+  if (p.k.regularization == 1) {
+    const float dr = (float)b - p.k.prior_r, di = (float)c - p.k.prior_i;
+    loss = loss + dr * dr + di * di;
+    alpha = 2.f * dr;
+    beta = 2.f * di;
+  }
+  st->chi2 = a;
+  st->s_r = (float)b;
+  st->s_i = (float)c;
+  st->alpha = alpha;
+  st->beta = beta;
+  st->last_loss = loss;
+  if (p.eval_only) return;
+
+  const int t = st->step;
+  // Keras local_step = iterations + 1; powers evaluated in double and rounded once
+  const double tt = (double)(t + 1);
+  const float b1p = (float)pow((double)p.k.beta1, tt);
+  if (p.k.optimizer == 0) {
+    st->lr_t = p.k.lr / (1.f - b1p);
+  } else if (p.k.optimizer == 1) {
+    const float b2p = (float)pow((double)p.k.beta2, tt);
+    st->lr_t = p.k.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+  } else {
+    st->lr_t = p.k.lr;
+  }
+  int snap = 0;
+  const int rec = t - p.k.n_skip;
+  if (rec >= 0) {
+    p.hist[rec] = loss;
+    st->nrec = rec + 1;
+    if (p.k.use_min && loss < st->min_loss) {
+      st->min_loss = loss;
+      snap = 1;
+      st->any_snap = 1;
+    }
+    if (rec >= 1 && fabs((double)(loss - st->prev_loss)) < p.k.tol) st->stop_after = t;
+    if (rec + 1 >= p.k.maxsteps) st->stop_after = t;
+    st->prev_loss = loss;
+  }
+  st->snap = snap;
+  st->upd_active = 1;
+  st->step = t + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimizer rules (Keras OptimizerV2; see oracle/restatement.py for provenance)
+//   SPARSE = the IndexedSlices form used for the gains, dense form for the coefficients
+// ------------------------------------------------------------------------------------------------
+template <bool SPARSE>
+__device__ __forceinline__ float opt_step(int optimizer, float theta, float g, float& m, float& u, float lr_t,
+                                          float beta1, float beta2, float eps) {
+  if (optimizer == 0) {  // Adamax
+    m = SPARSE ? (m * beta1 + g * (1.f - beta1)) : (m + (g - m) * (1.f - beta1));
+    u = fmaxf(u * beta2, fabsf(g));
+    return theta - lr_t * (m / (u + eps));
+  } else if (optimizer == 1) {  // Adam
+    m = SPARSE ? (m * beta1 + g * (1.f - beta1)) : (m + (g - m) * (1.f - beta1));
+    u = SPARSE ? (u * beta2 + (g * g) * (1.f - beta2)) : (u + (g * g - u) * (1.f - beta2));
+    return theta - (m * lr_t) / (sqrtf(u) + eps);
+  }
+  return theta - lr_t * g;  // SGD without momentum
+}
+
+struct GainsParams {
+  const float2* z;
+  const float2* y;
+  const int* ant_ptr;   // [nants + 1] CSR over antennas
+  const int* ant_ent;   // (baseline << 1) | side, ascending baseline order
+  const int* bl_ant0;
+  const int* bl_ant1;
+  float* g_r[2];
+  float* g_i[2];
+  float* m_r;
+  float* u_r;
+  float* m_i;
+  float* u_i;
+  float* snap_r;
+  float* snap_i;
+  float* grad_r;        // optional gradient output / all-reduce buffer
+  float* grad_i;
+  const FitState* st;
+  FitConsts k;
+  int nfp;
+  int nants;
+  int mode;             // 0: reduce + update; 1: reduce only -> grad; 2: update only from grad
+  int sum;
+  int eval;             // 1: stand-alone gradient evaluation (no step in flight)
+};
+
+__global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
+  const FitState* st = p.st;
+  int src;
+  if (p.eval) {
+    src = st->step & 1;  // stand-alone gradient evaluation at the current parameters
+  } else {
+    if (!st->upd_active) return;
+    src = (st->step - 1) & 1;
+  }
+  const int ant = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.nfp) return;
+  const float* __restrict__ gr = p.g_r[src];
+  const float* __restrict__ gi = p.g_i[src];
+  const size_t o = (size_t)ant * p.nfp + f;
+  float acc_r = 0.f, acc_i = 0.f;
+  if (p.mode != 2) {
+    const float alpha = st->alpha, beta = st->beta;
+    const int e0 = p.ant_ptr[ant], e1 = p.ant_ptr[ant + 1];
+    for (int e = e0; e < e1; ++e) {
+      const int ent = p.ant_ent[e];
+      const int b = ent >> 1, side = ent & 1;
+      const size_t ob = (size_t)b * p.nfp + f;
+      float2 z = p.z[ob];
+      if (p.sum) {
+        const float2 y = p.y[ob];
+        z.x += alpha * y.x + beta * y.y;
+        z.y += alpha * y.y - beta * y.x;
+      }
+      const int partner = side ? p.bl_ant0[b] : p.bl_ant1[b];
+      const size_t op = (size_t)partner * p.nfp + f;
+      const float pr = gr[op], pi = gi[op];
+      if (side == 0) {  // this antenna is ant0: conj(z) * g_partner
+        acc_r += z.x * pr + z.y * pi;
+        acc_i += z.x * pi - z.y * pr;
+      } else {          // this antenna is ant1: z * g_partner
+        acc_r += z.x * pr - z.y * pi;
+        acc_i += z.x * pi + z.y * pr;
+      }
+    }
+    if (p.grad_r) {
+      p.grad_r[o] = acc_r;
+      p.grad_i[o] = acc_i;
+    }
+    if (p.mode == 1) return;
+  } else {
+    acc_r = p.grad_r[o];
+    acc_i = p.grad_i[o];
+  }
+  float mr = p.m_r[o], ur = p.u_r[o], mi = p.m_i[o], ui = p.u_i[o];
+  const float nr = opt_step<true>(p.k.optimizer, gr[o], acc_r, mr, ur, st->lr_t, p.k.beta1, p.k.beta2, p.k.eps);
+  const float ni = opt_step<true>(p.k.optimizer, gi[o], acc_i, mi, ui, st->lr_t, p.k.beta1, p.k.beta2, p.k.eps);
+  p.m_r[o] = mr;
+  p.u_r[o] = ur;
+  p.m_i[o] = mi;
+  p.u_i[o] = ui;
+  p.g_r[src ^ 1][o] = nr;
+  p.g_i[src ^ 1][o] = ni;
+  if (st->snap && p.snap_r) {
+    p.snap_r[o] = nr;
+    p.snap_i[o] = ni;
+  }
+}
+
+struct CoeffParams {
+  const float* dcpart;
+  const int* coef_row0;   // [ncoef] global row of the coefficient in its group's first slot
+  const int* coef_grp;    // [ncoef]
+  const int* grp_nslots;
+  const int* grp_slot0;
+  const int* grp_coef0;
+  const int* slot_row0;
+  float* c_r;
+  float* c_i;
+  float* m_r;
+  float* u_r;
+  float* m_i;
+  float* u_i;
+  float* snap_r;
+  float* snap_i;
+  float* grad_r;
+  float* grad_i;
+  const FitState* st;
+  FitConsts k;
+  int ncoef;
+  int nq;
+  int mode;       // 0: update; 1: gradient only; 3: snapshot copy only (freeze_model)
+};
+
+__global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
+  const FitState* st = p.st;
+  if (p.mode != 1 && !st->upd_active) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.ncoef) return;
+  if (p.mode == 3) {
+    if (st->snap && p.snap_r) {
+      p.snap_r[c] = p.c_r[c];
+      p.snap_i[c] = p.c_i[c];
+    }
+    return;
+  }
+  const int grp = p.coef_grp[c];
+  const int ns = p.grp_nslots[grp];
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  {
+    const float* d = p.dcpart + (size_t)p.coef_row0[c] * p.nq;
+    t0 = d[0];
+    t1 = d[1];
+    if (p.nq == 4) {
+      t2 = d[2];
+      t3 = d[3];
+    }
+  }
+  if (ns > 1) {
+    const int k = c - p.grp_coef0[grp];
+    const int s0 = p.grp_slot0[grp];
+    for (int s = 1; s < ns; ++s) {
+      const float* d = p.dcpart + (size_t)(p.slot_row0[s0 + s] + k) * p.nq;
+      t0 += d[0];
+      t1 += d[1];
+      if (p.nq == 4) {
+        t2 += d[2];
+        t3 += d[3];
+      }
+    }
+  }
+  float gr = t0, gi = t1;
+  if (p.nq == 4) {
+    const float alpha = st->alpha, beta = st->beta;
+    gr = t0 + alpha * t2 - beta * t3;
+    gi = t1 + alpha * t3 + beta * t2;
+  }
+  if (p.grad_r) {
+    p.grad_r[c] = gr;
+    p.grad_i[c] = gi;
+  }
+  if (p.mode == 1) return;
+  float mr = p.m_r[c], ur = p.u_r[c], mi = p.m_i[c], ui = p.u_i[c];
+  const float nr = opt_step<false>(p.k.optimizer, p.c_r[c], gr, mr, ur, st->lr_t, p.k.beta1, p.k.beta2, p.k.eps);
+  const float ni = opt_step<false>(p.k.optimizer, p.c_i[c], gi, mi, ui, st->lr_t, p.k.beta1, p.k.beta2, p.k.eps);
+  p.m_r[c] = mr;
+  p.u_r[c] = ur;
+  p.m_i[c] = mi;
+  p.u_i[c] = ui;
+  p.c_r[c] = nr;
+  p.c_i[c] = ni;
+  if (st->snap && p.snap_r) {
+    p.snap_r[c] = nr;
+    p.snap_i[c] = ni;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup kernels
+// ------------------------------------------------------------------------------------------------
+struct RetileJob {
+  long long src_off;  // float offset in the staging buffer of the slot's [ncomp][nfreqs] block
+  long long dst_off;  // float offset of the item's tile 0
+  int ncomp;
+  int item_rows;
+  int row_in_item;
+  int pad;
+};
+
+// staging [ncomp][nfreqs] row-major  ->  tiled [tile][item_rows][FT]
+__global__ void retile_kernel(const float* __restrict__ staging, float* __restrict__ A, const RetileJob* jobs,
+                              int nfreqs, int ft) {
+  const RetileJob jb = jobs[blockIdx.x];
+  const long long n = (long long)jb.ncomp * nfreqs;
+  for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+    const int k = (int)(e / nfreqs), f = (int)(e % nfreqs);
+    const int tile = f / ft, fi = f % ft;
+    A[jb.dst_off + ((long long)tile * jb.item_rows + jb.row_in_item + k) * ft + fi] = staging[jb.src_off + e];
+  }
+}
+
+// [n][nfreqs] host layout <-> [n][nfp] padded device layout
+__global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int nfreqs, int nfp,
+                                float fill) {
+  const size_t row = blockIdx.x;
+  for (int f = threadIdx.x; f < nfp; f += blockDim.x)
+    dst[row * nfp + f] = f < nfreqs ? src[row * nfreqs + f] : fill;
+}
+__global__ void unpad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int nfreqs, int nfp) {
+  const size_t row = blockIdx.x;
+  for (int f = threadIdx.x; f < nfreqs; f += blockDim.x) dst[row * nfreqs + f] = src[row * nfp + f];
+}
+// per-baseline model: out[b][f] = vout[slot(b)][f]
+__global__ void model_gather_kernel(const float2* __restrict__ vout, const int* __restrict__ bl_slot,
+                                    float* __restrict__ out_r, float* __restrict__ out_i, int nfreqs, int nfp) {
+  const size_t b = blockIdx.x;
+  const size_t s = bl_slot[b];
+  for (int f = threadIdx.x; f < nfreqs; f += blockDim.x) {
+    const float2 v = vout[s * nfp + f];
+    out_r[b * nfreqs + f] = v.x;
+    out_i[b * nfreqs + f] = v.y;
+  }
+}
+
+// Deterministic two-stage sum of x[i]*y[i] (prior sums, calibration.py:620-625) and of
+// w[i] * (v_r^2 + v_i^2) (SNR weights, calibration.py:1238-1241).
+__global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                          size_t n, double* __restrict__ out) {
+  __shared__ double sh[8];
+  double a = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    a += (double)(y ? x[i] * y[i] : x[i]);
+  for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    out[blockIdx.x] = t;
+  }
+}
+
+__global__ void snr_weight_kernel(float* __restrict__ w, const float2* __restrict__ vout,
+                                  const int* __restrict__ bl_slot, int nfp, float scale) {
+  const size_t b = blockIdx.x;
+  const size_t s = bl_slot[b];
+  for (int f = threadIdx.x; f < nfp; f += blockDim.x) {
+    const float2 v = vout[s * nfp + f];
+    const float nw = (v.x * v.x + v.y * v.y) * w[b * nfp + f];
+    w[b * nfp + f] = nw * scale;
+  }
+}
+__global__ void scale_kernel(float* __restrict__ x, size_t n, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = x[i] / scale;
+}
+
+}  // namespace calb2

@@ -1,0 +1,166 @@
+"""Python handle on a native fit plan (one GPU).  Thin: every method is one C-ABI call."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+OPTIMIZER_IDS = {"Adamax": 0, "Adam": 1, "SGD": 2}
+# tf.keras.optimizers defaults (TensorFlow >= 2.4 OptimizerV2), used when **opt_kwargs omits a field
+KERAS_DEFAULTS = {
+    "Adamax": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
+    "Adam": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
+    "SGD": dict(learning_rate=0.01),
+}
+# names the reference's OPTIMIZERS dict accepts (calibration.py:17-27); those without a device
+# implementation raise NotImplementedError instead of silently substituting something else
+REFERENCE_OPTIMIZERS = ("Adadelta", "Adam", "Adamax", "Ftrl", "Nadam", "SGD", "RMSprop", "Adagrad", "LAMB")
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class FitPlan:
+    """Device-resident basis + per-integration state.  Mirrors calibration.py:1143-1152 (create) and
+    the per-integration calls of 1184-1300."""
+
+    def __init__(self, layout, device=0, tile_freqs=0, basis_batch=2048):
+        self._lib = nat.load()
+        self.layout = layout
+        self._handle = C.c_void_p()
+        desc = nat.PlanDesc(
+            device=device, nants=layout.nants, nfreqs=layout.nfreqs, ngroups=layout.ngroups,
+            group_ncomp=nat.iptr(layout.group_ncomp), group_nslots=nat.iptr(layout.group_nslots),
+            slot_nbls=nat.iptr(layout.slot_nbls), bl_ant0=nat.iptr(layout.bl_ant0), bl_ant1=nat.iptr(layout.bl_ant1),
+            tile_freqs=tile_freqs,
+        )
+        nat.check(self._lib.calb2_plan_create(C.byref(desc), C.byref(self._handle)))
+        for g0 in range(0, layout.ngroups, basis_batch):
+            blks = layout.blocks[g0 : g0 + basis_batch]
+            ptrs = (C.c_void_p * len(blks))(*[b.ctypes.data if b.size else None for b in blks])
+            nat.check(self._lib.calb2_plan_set_basis(self._handle, g0, len(blks), ptrs))
+        info = nat.PlanInfo()
+        nat.check(self._lib.calb2_plan_get_info(self._handle, C.byref(info)))
+        self.info = {name: getattr(info, name) for name, _ in nat.PlanInfo._fields_}
+
+    # -- lifetime
+    def close(self):
+        if self._handle:
+            self._lib.calb2_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- per integration
+    def set_integration(self, data_r, data_i, wgts):
+        d_r, d_i, w = _f32(data_r), _f32(data_i), _f32(wgts)
+        assert d_r.shape == (self.layout.nbls, self.layout.nfreqs), d_r.shape
+        nat.check(self._lib.calb2_set_integration(self._handle, nat.fptr(d_r), nat.fptr(d_i), nat.fptr(w)))
+
+    def set_gains(self, g_r, g_i):
+        g_r, g_i = _f32(g_r), _f32(g_i)
+        assert g_r.shape == (self.layout.nants, self.layout.nfreqs), g_r.shape
+        nat.check(self._lib.calb2_set_gains(self._handle, nat.fptr(g_r), nat.fptr(g_i)))
+
+    def set_coeffs(self, coef_r, coef_i):
+        c_r, c_i = _f32(coef_r), _f32(coef_i)
+        assert c_r.shape == (self.layout.ncoef,), c_r.shape
+        nat.check(self._lib.calb2_set_coeffs(self._handle, nat.fptr(c_r), nat.fptr(c_i)))
+
+    def init_coeffs(self, sky_r, sky_i):
+        s_r, s_i = _f32(sky_r), _f32(sky_i)
+        nat.check(self._lib.calb2_init_coeffs(self._handle, nat.fptr(s_r), nat.fptr(s_i)))
+
+    def prior_sums(self, sky_r, sky_i):
+        s_r, s_i = _f32(sky_r), _f32(sky_i)
+        pr, pi = C.c_float(), C.c_float()
+        nat.check(self._lib.calb2_prior_sums(self._handle, nat.fptr(s_r), nat.fptr(s_i), C.byref(pr), C.byref(pi)))
+        return np.float32(pr.value), np.float32(pi.value)
+
+    def apply_model_snr_weights(self):
+        nat.check(self._lib.calb2_apply_model_snr_weights(self._handle))
+
+    # -- the loop
+    def fit(self, optimizer="Adamax", maxsteps=10000, tol=1e-14, use_min=False, freeze_model=False,
+            model_regularization=None, prior_r_sum=0.0, prior_i_sum=0.0, n_profile_steps=0, steps_per_sync=0,
+            use_graph=False, **opt_kwargs):
+        if optimizer not in REFERENCE_OPTIMIZERS:
+            raise KeyError(optimizer)  # calibration.py:571: OPTIMIZERS[optimizer]
+        if optimizer not in OPTIMIZER_IDS:
+            raise NotImplementedError(f"optimizer {optimizer!r} has no device implementation yet")
+        hp = dict(KERAS_DEFAULTS[optimizer])
+        unknown = set(opt_kwargs) - set(hp)
+        if unknown:
+            raise TypeError(f"unexpected optimizer arguments for {optimizer}: {sorted(unknown)}")
+        hp.update(opt_kwargs)
+        opts = nat.FitOptions(
+            optimizer=OPTIMIZER_IDS[optimizer], learning_rate=hp["learning_rate"], beta_1=hp.get("beta_1", 0.0),
+            beta_2=hp.get("beta_2", 0.0), epsilon=hp.get("epsilon", 0.0), maxsteps=int(maxsteps), tol=float(tol),
+            use_min=int(bool(use_min)), freeze_model=int(bool(freeze_model)),
+            regularization=1 if model_regularization == "sum" else 0, prior_r_sum=float(prior_r_sum),
+            prior_i_sum=float(prior_i_sum), n_profile_steps=int(n_profile_steps), steps_per_sync=int(steps_per_sync),
+            use_graph=int(bool(use_graph)),
+        )
+        hist = np.zeros(max(1, int(maxsteps)), dtype=np.float32)
+        res = nat.FitResult()
+        nat.check(self._lib.calb2_fit(self._handle, C.byref(opts), nat.fptr(hist), C.byref(res)))
+        result = {name: getattr(res, name) for name, _ in nat.FitResult._fields_}
+        return hist[: res.nsteps_recorded].copy(), result
+
+    def loss_and_grads(self, model_regularization=None, prior_r_sum=0.0, prior_i_sum=0.0):
+        lay = self.layout
+        loss = C.c_float()
+        dg_r = np.zeros((lay.nants, lay.nfreqs), dtype=np.float32)
+        dg_i = np.zeros_like(dg_r)
+        dc_r = np.zeros(lay.ncoef, dtype=np.float32)
+        dc_i = np.zeros_like(dc_r)
+        nat.check(self._lib.calb2_loss_and_grads(
+            self._handle, 1 if model_regularization == "sum" else 0, float(prior_r_sum), float(prior_i_sum),
+            C.byref(loss), nat.fptr(dg_r), nat.fptr(dg_i), nat.fptr(dc_r), nat.fptr(dc_i)))
+        return np.float32(loss.value), dg_r, dg_i, dc_r, dc_i
+
+    # -- results
+    def get_gains(self):
+        g_r = np.zeros((self.layout.nants, self.layout.nfreqs), dtype=np.float32)
+        g_i = np.zeros_like(g_r)
+        nat.check(self._lib.calb2_get_gains(self._handle, nat.fptr(g_r), nat.fptr(g_i)))
+        return g_r, g_i
+
+    def get_coeffs(self):
+        c_r = np.zeros(self.layout.ncoef, dtype=np.float32)
+        c_i = np.zeros_like(c_r)
+        nat.check(self._lib.calb2_get_coeffs(self._handle, nat.fptr(c_r), nat.fptr(c_i)))
+        return c_r, c_i
+
+    def get_model(self):
+        m_r = np.zeros((self.layout.nbls, self.layout.nfreqs), dtype=np.float32)
+        m_i = np.zeros_like(m_r)
+        nat.check(self._lib.calb2_get_model(self._handle, nat.fptr(m_r), nat.fptr(m_i)))
+        return m_r, m_i
+
+    def get_weights(self):
+        w = np.zeros((self.layout.nbls, self.layout.nfreqs), dtype=np.float32)
+        nat.check(self._lib.calb2_get_weights(self._handle, nat.fptr(w)))
+        return w
+
+    # -- multi-GPU
+    def comm_init(self, unique_id, rank, nranks):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        nat.check(self._lib.calb2_comm_init(self._handle, C.cast(buf, C.c_void_p), rank, nranks, nat.find_nccl().encode()))
+
+
+def nccl_unique_id():
+    buf = (C.c_char * 128)()
+    nat.check(nat.load().calb2_comm_unique_id(C.cast(buf, C.c_void_p), nat.find_nccl().encode()))
+    return bytes(buf)

@@ -1,0 +1,162 @@
+/*
+ * calamity_b200 -- C ABI of the B200-native gain-and-foreground fit.
+ *
+ * The reference (aewallwi/calamity) is pure Python over TensorFlow and has no FFI seam of its own; the
+ * seam this library is bound at is the call `fit_gains_and_foregrounds(...)` made from
+ * `calibrate_and_model_tensor` (/root/reference/calamity/calibration.py:1244-1269) together with the
+ * tensor builders around it.  Each entry point below names the reference lines it replaces.
+ *
+ * Conventions: plain C, every function returns 0 on success and a negative code on failure
+ * (`calb2_last_error()` gives the message of the calling thread's last failure); no exception crosses
+ * the ABI; the caller owns every host buffer, the library owns all device memory; a plan is bound to
+ * one device and must be driven by one host thread at a time.  All floating point buffers are IEEE
+ * float32 (the reference's default `dtype=np.float32`, calibration.py:974), all indices int32.
+ *
+ * Canonical orderings (they are exactly the reference's flattening of its chunked tensors):
+ *   groups     : chunk-major, then group index inside the chunk        (calibration.py:165-170)
+ *   slots      : per group, its redundant sub-groups in key order       (calibration.py:173)
+ *   baselines  : per slot, its antenna pairs in key order               (calibration.py:175-184)
+ *   coefficients: per group, component k = 0..ncomp-1                   (calibration.py:906)
+ * so `data_r/data_i/wgts` are the per-chunk [ngrps, nbls, nfreqs] tensors of `tensorize_data`
+ * (calibration.py:305-308) concatenated, and `coef_r/coef_i` are the non-padding entries of the
+ * per-chunk [nvecs, ngrps, 1, 1] tensors of `tensorize_fg_coeffs`.
+ */
+#ifndef CALAMITY_B200_H
+#define CALAMITY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct calb2_plan calb2_plan;
+
+enum {
+  CALB2_OK = 0,
+  CALB2_ERR_ARG = -1,      /* bad argument / inconsistent description */
+  CALB2_ERR_CUDA = -2,     /* a CUDA runtime call failed */
+  CALB2_ERR_UNSUPPORTED = -3,
+  CALB2_ERR_STATE = -4,    /* call order violated (e.g. fit before set_integration) */
+  CALB2_ERR_NCCL = -5,
+  CALB2_ERR_NONFINITE = -6
+};
+
+/* tf.optimizers.* of calibration.py:17-27 that have a device implementation. */
+enum { CALB2_OPT_ADAMAX = 0, CALB2_OPT_ADAM = 1, CALB2_OPT_SGD = 2 };
+
+/* model_regularization of calibration.py:619-661: anything but "sum" is the plain chi-squared. */
+enum { CALB2_REG_NONE = 0, CALB2_REG_SUM = 1 };
+
+/* Ragged description of the foreground basis: replaces the dense zero-padded tensors built by
+ * tensorize_fg_model_comps_dict (calibration.py:104-190) and the index lists of 577-594. */
+typedef struct {
+  int32_t device;            /* CUDA device ordinal */
+  int32_t nants;             /* g_r.shape[0]  (calibration.py:575) */
+  int32_t nfreqs;            /* g_r.shape[1]  (calibration.py:576) */
+  int32_t ngroups;           /* fitting groups, all chunks */
+  const int32_t* group_ncomp;   /* [ngroups]  basis vectors actually stored for the group (no zero padding) */
+  const int32_t* group_nslots;  /* [ngroups]  redundant sub-groups sharing the group's coefficients */
+  const int32_t* slot_nbls;     /* [sum nslots] baselines per slot (they share one model visibility) */
+  const int32_t* bl_ant0;       /* [nbls_total] corr_inds[..][0] in canonical order */
+  const int32_t* bl_ant1;       /* [nbls_total] corr_inds[..][1] */
+  int32_t tile_freqs;        /* 0 = choose; else 16, 32 or 64 channels per staged tile */
+} calb2_plan_desc;
+
+/* Options of fit_gains_and_foregrounds (calibration.py:447-473). */
+typedef struct {
+  int32_t optimizer;         /* CALB2_OPT_*            (`optimizer`, calibration.py:460, 571) */
+  float learning_rate;       /* Keras names, forwarded verbatim by **opt_kwargs (calibration.py:472) */
+  float beta_1;
+  float beta_2;
+  float epsilon;
+  int32_t maxsteps;          /* calibration.py:459, 699 */
+  double tol;                /* calibration.py:458, 712 */
+  int32_t use_min;           /* calibration.py:457, 702-710 */
+  int32_t freeze_model;      /* calibration.py:461, 598-603 */
+  int32_t regularization;    /* CALB2_REG_*            (calibration.py:470, 619) */
+  float prior_r_sum;         /* sum(sky_model_r * wgts), calibration.py:620-625 */
+  float prior_i_sum;
+  int32_t n_profile_steps;   /* extra real steps before the warm-up step (calibration.py:681-687) */
+  int32_t steps_per_sync;    /* 0 = default; iterations enqueued between host checks of the stop flag */
+  int32_t use_graph;         /* 1 = replay a captured CUDA graph of steps_per_sync iterations */
+} calb2_fit_options;
+
+typedef struct {
+  int32_t nsteps_recorded;   /* len(fit_history["loss"]) */
+  int32_t nsteps_total;      /* optimizer updates applied = n_profile_steps + 1 + recorded */
+  float final_loss;          /* min_loss echoed at calibration.py:734-737 */
+  float loop_ms;             /* device time of the whole step loop (CUDA events on the plan's stream) */
+  float heavy_ms;            /* device time spent in the fused basis-streaming kernel alone */
+  int64_t heavy_launches;
+  int64_t kernel_launches;   /* all kernels launched inside the loop */
+} calb2_fit_result;
+
+/* Sizes of the plan's internal layout, for roofline accounting. */
+typedef struct {
+  int64_t n_d;        /* nbls_total * nfreqs */
+  int64_t n_a_nz;     /* sum over slots ncomp * nfreqs  (unique non-padding basis elements) */
+  int64_t n_a_stored; /* basis floats actually resident (adds row/channel alignment padding) */
+  int64_t n_c_nz;     /* sum over groups ncomp */
+  int64_t nbls_total;
+  int64_t nslots_total;
+  int64_t nitems;     /* CTAs of the fused kernel */
+  int32_t tile_freqs;
+  int32_t rows_per_item_max;
+  int64_t device_bytes;
+} calb2_plan_info;
+
+const char* calb2_last_error(void);
+const char* calb2_version(void);
+
+/* Once per calibrate_and_model_tensor call: mirrors calibration.py:1143-1152. */
+int calb2_plan_create(const calb2_plan_desc* desc, calb2_plan** out);
+int calb2_plan_destroy(calb2_plan* plan);
+int calb2_plan_get_info(const calb2_plan* plan, calb2_plan_info* info);
+
+/* Upload basis vectors for groups [group_first, group_first + ngroups): blocks[i] points at the
+ * group's float32 [nslots][ncomp][nfreqs] block (row k of slot s = fg_model_comps[c][k, g, b, :] for any
+ * baseline b of slot s, calibration.py:178-183).  Equal pointers are uploaded once. */
+int calb2_plan_set_basis(calb2_plan* plan, int32_t group_first, int32_t ngroups, const float* const* blocks);
+
+/* Per integration: mirrors tensorize_data's outputs (calibration.py:1184-1194), [nbls_total][nfreqs]. */
+int calb2_set_integration(calb2_plan* plan, const float* data_r, const float* data_i, const float* wgts);
+/* tensorize_gains outputs (calibration.py:1213) [nants][nfreqs]; coefficient vectors [n_c_nz]. */
+int calb2_set_gains(calb2_plan* plan, const float* g_r, const float* g_i);
+int calb2_set_coeffs(calb2_plan* plan, const float* coef_r, const float* coef_i);
+
+/* tensorize_fg_coeffs (calibration.py:828-913) run on the device for both parts at once: least squares
+ * of (sky * (wgts != 0)) on each group's basis.  Uses the weights given to calb2_set_integration. */
+int calb2_init_coeffs(calb2_plan* plan, const float* sky_r, const float* sky_i);
+/* sum(sky_model * wgts) of calibration.py:620-625, reduced on the device. */
+int calb2_prior_sums(calb2_plan* plan, const float* sky_r, const float* sky_i, float* prior_r, float* prior_i);
+/* use_model_snr_weights block, calibration.py:1235-1242: w <- w (v_r^2 + v_i^2) / sum. */
+int calb2_apply_model_snr_weights(calb2_plan* plan);
+
+/* The loop of fit_gains_and_foregrounds, calibration.py:571-738.  loss_history has room for
+ * opts->maxsteps floats; the first result->nsteps_recorded are filled (fit_history["loss"]). */
+int calb2_fit(calb2_plan* plan, const calb2_fit_options* opts, float* loss_history, calb2_fit_result* result);
+
+/* One evaluation of loss and gradient at the current parameters without updating them (the
+ * tape.gradient call of calibration.py:664-666); any output pointer may be NULL. */
+int calb2_loss_and_grads(calb2_plan* plan, int32_t regularization, float prior_r_sum, float prior_i_sum,
+                         float* loss, float* dg_r, float* dg_i, float* dcoef_r, float* dcoef_i);
+
+/* g_r_opt, g_i_opt, fg_r_opt, fg_i_opt of calibration.py:738. */
+int calb2_get_gains(calb2_plan* plan, float* g_r, float* g_i);
+int calb2_get_coeffs(calb2_plan* plan, float* coef_r, float* coef_i);
+/* Foreground model visibilities sum_k c_k A_k per baseline, [nbls_total][nfreqs]; the caller scatters
+ * them into the [nants, nants, nfreqs] cube of yield_fg_model_array (calibration.py:402-444). */
+int calb2_get_model(calb2_plan* plan, float* model_r, float* model_i);
+int calb2_get_weights(calb2_plan* plan, float* wgts);
+
+/* Multi-GPU: the plan holds one rank's share of the groups; the per-iteration
+ * gain gradient, loss and regulariser sums are all-reduced over NCCL.  `nccl_unique_id` is the 128-byte
+ * ncclUniqueId created on rank 0 and broadcast by the caller. */
+int calb2_comm_init(calb2_plan* plan, const void* nccl_unique_id, int32_t rank, int32_t nranks, const char* nccl_lib);
+int calb2_comm_unique_id(void* nccl_unique_id_out, const char* nccl_lib);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CALAMITY_B200_H */
