@@ -113,7 +113,7 @@ struct calb2_plan {
   DevBuf<double> partials, red_d;
   DevBuf<ItemDesc> d_items;
   DevBuf<unsigned char> row_slot;
-  DevBuf<int> row_coef, d_slot_row0, d_slot_bl0, d_bl_ant0, d_bl_ant1, d_bl_slot, ant_ptr, ant_ent, coef_row0, coef_grp,
+  DevBuf<int> row_coef, d_slot_row0, d_slot_bl0, d_bl_ant0, d_bl_ant1, d_bl_slot, ant_ptr, ant_ent, coef_row0, coef_grp, ant_partner,
       d_grp_nslots, d_grp_slot0, d_grp_coef0, d_grp_ncomp;
   DevBuf<FitState> state, state_eval;
   DevBuf<SlotGeom> slot_geom;
@@ -234,6 +234,7 @@ static GainsParams gains_params(calb2_plan* pl, const FitState* st, const FitCon
   gp.y = pl->y.p;
   gp.ant_ptr = pl->ant_ptr.p;
   gp.ant_ent = pl->ant_ent.p;
+  gp.ant_partner = pl->ant_partner.p;
   gp.bl_ant0 = pl->d_bl_ant0.p;
   gp.bl_ant1 = pl->d_bl_ant1.p;
   for (int b = 0; b < 2; ++b) {
@@ -602,7 +603,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
       coef_row0[pl->grp_coef0[g] + k] = pl->slot_row0[pl->grp_slot0[g]] + k;
       coef_grp[pl->grp_coef0[g] + k] = g;
     }
-  std::vector<int> ant_ptr(d->nants + 1, 0), ant_ent(2 * nb);
+  std::vector<int> ant_ptr(d->nants + 1, 0), ant_ent(2 * nb), ant_partner(2 * nb);
   for (long long b = 0; b < nb; ++b) {
     ant_ptr[pl->bl_ant0[b] + 1]++;
     ant_ptr[pl->bl_ant1[b] + 1]++;
@@ -611,7 +612,9 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   {
     std::vector<int> fill(ant_ptr.begin(), ant_ptr.end() - 1);
     for (long long b = 0; b < nb; ++b) {  // ascending baseline order inside every antenna's list
+      ant_partner[fill[pl->bl_ant0[b]]] = pl->bl_ant1[b];
       ant_ent[fill[pl->bl_ant0[b]]++] = (int)(b << 1);
+      ant_partner[fill[pl->bl_ant1[b]]] = pl->bl_ant0[b];
       ant_ent[fill[pl->bl_ant1[b]]++] = (int)(b << 1) | 1;
     }
   }
@@ -641,6 +644,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(upload(pl->d_bl_slot, pl->bl_slot, pl));
   TRY(upload(pl->ant_ptr, ant_ptr, pl));
   TRY(upload(pl->ant_ent, ant_ent, pl));
+  TRY(upload(pl->ant_partner, ant_partner, pl));
   TRY(upload(pl->coef_row0, coef_row0, pl));
   TRY(upload(pl->coef_grp, coef_grp, pl));
   TRY(upload(pl->d_grp_nslots, pl->grp_nslots, pl));
@@ -709,7 +713,7 @@ int calb2_plan_destroy(calb2_plan* pl) {
   pl->d_items.release();
   pl->row_slot.release();
   DevBuf<int>* ib[] = {&pl->row_coef, &pl->d_slot_row0, &pl->d_slot_bl0, &pl->d_bl_ant0, &pl->d_bl_ant1, &pl->d_bl_slot,
-                       &pl->ant_ptr, &pl->ant_ent, &pl->coef_row0, &pl->coef_grp, &pl->d_grp_nslots, &pl->d_grp_slot0,
+                       &pl->ant_ptr, &pl->ant_ent, &pl->ant_partner, &pl->coef_row0, &pl->coef_grp, &pl->d_grp_nslots, &pl->d_grp_slot0,
                        &pl->d_grp_coef0, &pl->d_grp_ncomp};
   for (auto* b : ib) b->release();
   pl->state.release();

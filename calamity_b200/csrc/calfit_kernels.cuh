@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     mbar_fence_init();
+    mbar_expect_tx(&mbar[0], tile_bytes);  // tile 0 streams in while the item's metadata is gathered
+    bulk_g2s(Abuf, Abase, tile_bytes, &mbar[0]);
   }
   for (int r = tid; r < it.nrows; r += C::NTHR) {
     const int ci = p.row_coef[it.row0 + r];
@@ -207,10 +209,35 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
     slot_bl0[s] = p.slot_bl0[it.slot0 + s];
   }
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&mbar[0], tile_bytes);
-    bulk_g2s(Abuf, Abase, tile_bytes, &mbar[0]);
-  }
+
+  // Q-phase inputs of the first baseline of each (slot, channel) element this thread owns are prefetched
+  // into registers one tile ahead: issued right after Q(j) for tile j + 1, so their DRAM/L2 latency is
+  // covered by phase B, the tile wait and phase F instead of being exposed in every tile.
+  constexpr int EPT = (C::SMAX * FT + C::NTHR - 1) / C::NTHR;
+  float pf[EPT][7];
+  auto prefetch_q = [&](int jt) {
+#pragma unroll
+    for (int m = 0; m < EPT; ++m) {
+      const int e = tid + m * C::NTHR;
+      if (e < it.nslots * FT) {
+        const int s = e / FT, f = e % FT;
+        const int b = slot_bl0[s];
+        if (b < slot_bl0[s + 1]) {
+          const int fg = jt * FT + f;
+          const size_t o = (size_t)b * p.nfp + fg;
+          pf[m][0] = p.d_r[o];
+          pf[m][1] = p.d_i[o];
+          pf[m][2] = p.w[o];
+          const size_t o0 = (size_t)p.bl_ant0[b] * p.nfp + fg, o1 = (size_t)p.bl_ant1[b] * p.nfp + fg;
+          pf[m][3] = g_r[o0];
+          pf[m][4] = g_i[o0];
+          pf[m][5] = g_r[o1];
+          pf[m][6] = g_i[o1];
+        }
+      }
+    }
+  };
+  prefetch_q(0);
 
   float acc[RPT][NQ];
 #pragma unroll
@@ -272,53 +299,65 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
     __syncthreads();
 
     // ---------------- phase Q: gains, model, residual, chi^2, dL/dv ----------------
-    for (int e = tid; e < it.nslots * FT; e += C::NTHR) {
-      const int s = e / FT, f = e % FT;
-      const int fg = j * FT + f;
-      const int w_lo = slot_step0[s] / RPT, w_hi = (slot_step0[s + 1] - 1) / RPT;
-      float v_r = 0.f, v_i = 0.f;
-      for (int w = w_lo; w <= w_hi; ++w) {
-        v_r += vpart[((w + s) * 2 + 0) * FT + f];
-        v_i += vpart[((w + s) * 2 + 1) * FT + f];
-      }
-      float qr = 0.f, qi = 0.f, pw = 0.f, qw = 0.f;
-      for (int b = slot_bl0[s]; b < slot_bl0[s + 1]; ++b) {
-        const size_t o = (size_t)b * p.nfp + fg;
-        const float dr = p.d_r[o], di = p.d_i[o], w = p.w[o];
-        if (p.init_mode) {  // right-hand side of the coefficient initialisation: data * (w != 0)
-          const float msk = (fabsf(w) <= 1e-8f) ? 0.f : 1.f;  // np.isclose(w, 0): |w| <= atol = 1e-8
-          qr += dr * msk;
-          qi += di * msk;
-          continue;
+#pragma unroll
+    for (int m = 0; m < EPT; ++m) {
+      const int e = tid + m * C::NTHR;
+      if (e < it.nslots * FT) {
+        const int s = e / FT, f = e % FT;
+        const int fg = j * FT + f;
+        const int w_lo = slot_step0[s] / RPT, w_hi = (slot_step0[s + 1] - 1) / RPT;
+        float v_r = 0.f, v_i = 0.f;
+        for (int w = w_lo; w <= w_hi; ++w) {
+          v_r += vpart[((w + s) * 2 + 0) * FT + f];
+          v_i += vpart[((w + s) * 2 + 1) * FT + f];
         }
-        const size_t o0 = (size_t)p.bl_ant0[b] * p.nfp + fg, o1 = (size_t)p.bl_ant1[b] * p.nfp + fg;
-        const float gr0 = g_r[o0], gi0 = g_i[o0], gr1 = g_r[o1], gi1 = g_i[o1];
-        const float P = gr0 * gr1 + gi0 * gi1;
-        const float Q = gr0 * gi1 - gi0 * gr1;
-        const float mr = P * v_r + Q * v_i;
-        const float mi = P * v_i - Q * v_r;
-        const float rr = dr - mr, ri = di - mi;
-        loss_acc += (rr * rr + ri * ri) * w;
-        const float er = -2.f * w * rr, ei = -2.f * w * ri;
-        p.z[o] = make_float2(er * v_r + ei * v_i, er * v_i - ei * v_r);
-        qr += P * er - Q * ei;
-        qi += Q * er + P * ei;
+        float qr = 0.f, qi = 0.f, pw = 0.f, qw = 0.f;
+        const int b_first = slot_bl0[s], b_end = slot_bl0[s + 1];
+        for (int b = b_first; b < b_end; ++b) {
+          const size_t o = (size_t)b * p.nfp + fg;
+          float dr, di, w, gr0, gi0, gr1, gi1;
+          if (b == b_first) {
+            dr = pf[m][0]; di = pf[m][1]; w = pf[m][2];
+            gr0 = pf[m][3]; gi0 = pf[m][4]; gr1 = pf[m][5]; gi1 = pf[m][6];
+          } else {
+            dr = p.d_r[o]; di = p.d_i[o]; w = p.w[o];
+            const size_t o0 = (size_t)p.bl_ant0[b] * p.nfp + fg, o1 = (size_t)p.bl_ant1[b] * p.nfp + fg;
+            gr0 = g_r[o0]; gi0 = g_i[o0]; gr1 = g_r[o1]; gi1 = g_i[o1];
+          }
+          if (p.init_mode) {  // right-hand side of the coefficient initialisation: data * (w != 0)
+            const float msk = (fabsf(w) <= 1e-8f) ? 0.f : 1.f;  // np.isclose(w, 0): |w| <= atol = 1e-8
+            qr += dr * msk;
+            qi += di * msk;
+            continue;
+          }
+          const float P = gr0 * gr1 + gi0 * gi1;
+          const float Q = gr0 * gi1 - gi0 * gr1;
+          const float mr = P * v_r + Q * v_i;
+          const float mi = P * v_i - Q * v_r;
+          const float rr = dr - mr, ri = di - mi;
+          loss_acc += (rr * rr + ri * ri) * w;
+          const float er = -2.f * w * rr, ei = -2.f * w * ri;
+          p.z[o] = make_float2(er * v_r + ei * v_i, er * v_i - ei * v_r);
+          qr += P * er - Q * ei;
+          qi += Q * er + P * ei;
+          if (SUM) {
+            p.y[o] = make_float2(w * v_r, w * v_i);
+            sr_acc += w * mr;
+            si_acc += w * mi;
+            pw += P * w;
+            qw += Q * w;
+          }
+        }
+        qbuf[(s * NQ + 0) * FT + f] = qr;
+        qbuf[(s * NQ + 1) * FT + f] = qi;
         if (SUM) {
-          p.y[o] = make_float2(w * v_r, w * v_i);
-          sr_acc += w * mr;
-          si_acc += w * mi;
-          pw += P * w;
-          qw += Q * w;
+          qbuf[(s * NQ + 2) * FT + f] = pw;
+          qbuf[(s * NQ + 3) * FT + f] = qw;
         }
+        if (p.store_v) p.vout[(size_t)(it.slot0 + s) * p.nfp + fg] = make_float2(v_r, v_i);
       }
-      qbuf[(s * NQ + 0) * FT + f] = qr;
-      qbuf[(s * NQ + 1) * FT + f] = qi;
-      if (SUM) {
-        qbuf[(s * NQ + 2) * FT + f] = pw;
-        qbuf[(s * NQ + 3) * FT + f] = qw;
-      }
-      if (p.store_v) p.vout[(size_t)(it.slot0 + s) * p.nfp + fg] = make_float2(v_r, v_i);
     }
+    if (j + 1 < p.ntiles) prefetch_q(j + 1);
     __syncthreads();
 
     // ---------------- phase B: backward contraction, accumulated in registers ----------------
@@ -516,6 +555,7 @@ struct GainsParams {
   const float2* y;
   const int* ant_ptr;   // [nants + 1] CSR over antennas
   const int* ant_ent;   // (baseline << 1) | side, ascending baseline order
+  const int* ant_partner;  // the other antenna of that baseline
   const int* bl_ant0;
   const int* bl_ant1;
   float* g_r[2];
@@ -556,26 +596,47 @@ __global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
   if (p.mode != 2) {
     const float alpha = st->alpha, beta = st->beta;
     const int e0 = p.ant_ptr[ant], e1 = p.ant_ptr[ant + 1];
-    for (int e = e0; e < e1; ++e) {
-      const int ent = p.ant_ent[e];
-      const int b = ent >> 1, side = ent & 1;
-      const size_t ob = (size_t)b * p.nfp + f;
-      float2 z = p.z[ob];
+    auto accumulate = [&](int ent, float2 z, float2 y, float pr, float pi) {
       if (p.sum) {
-        const float2 y = p.y[ob];
         z.x += alpha * y.x + beta * y.y;
         z.y += alpha * y.y - beta * y.x;
       }
-      const int partner = side ? p.bl_ant0[b] : p.bl_ant1[b];
-      const size_t op = (size_t)partner * p.nfp + f;
-      const float pr = gr[op], pi = gi[op];
-      if (side == 0) {  // this antenna is ant0: conj(z) * g_partner
+      if ((ent & 1) == 0) {  // this antenna is ant0: conj(z) * g_partner
         acc_r += z.x * pr + z.y * pi;
         acc_i += z.x * pi - z.y * pr;
-      } else {          // this antenna is ant1: z * g_partner
+      } else {               // this antenna is ant1: z * g_partner
         acc_r += z.x * pr - z.y * pi;
         acc_i += z.x * pi + z.y * pr;
       }
+    };
+    constexpr int U = 8;  // independent loads in flight per thread; the summation order stays e0..e1-1
+    int e = e0;
+    for (; e + U <= e1; e += U) {
+      int ent[U], par[U];
+      float2 zz[U], yy[U];
+      float pr[U], pi[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        ent[k] = p.ant_ent[e + k];
+        par[k] = p.ant_partner[e + k];
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const size_t ob = (size_t)(ent[k] >> 1) * p.nfp + f;
+        const size_t op = (size_t)par[k] * p.nfp + f;
+        zz[k] = p.z[ob];
+        yy[k] = p.sum ? p.y[ob] : make_float2(0.f, 0.f);
+        pr[k] = gr[op];
+        pi[k] = gi[op];
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) accumulate(ent[k], zz[k], yy[k], pr[k], pi[k]);
+    }
+    for (; e < e1; ++e) {
+      const int ent = p.ant_ent[e];
+      const size_t ob = (size_t)(ent >> 1) * p.nfp + f;
+      const size_t op = (size_t)p.ant_partner[e] * p.nfp + f;
+      accumulate(ent, p.z[ob], p.sum ? p.y[ob] : make_float2(0.f, 0.f), gr[op], gi[op]);
     }
     if (p.grad_r) {
       p.grad_r[o] = acc_r;
