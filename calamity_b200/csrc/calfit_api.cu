@@ -591,6 +591,10 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   pl->slot_row0[ns] = (int)rows;
   pl->rows_total = rows;
   pl->a_floats = rows * (long long)pl->nfp;
+  if (nb * (long long)pl->nfp > INT_MAX) {
+    delete pl;
+    return fail(CALB2_ERR_UNSUPPORTED, "nbls * nfreqs = %lld exceeds the 32-bit element index of the fused kernel", nb * (long long)pl->nfp);
+  }
   if (rows > INT_MAX / 4) {
     delete pl;
     return fail(CALB2_ERR_UNSUPPORTED, "too many basis rows (%lld)", rows);

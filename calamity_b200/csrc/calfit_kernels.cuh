@@ -199,9 +199,23 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
     mbar_expect_tx(&mbar[0], tile_bytes);  // tile 0 streams in while the item's metadata is gathered
     bulk_g2s(Abuf, Abase, tile_bytes, &mbar[0]);
   }
-  for (int r = tid; r < it.nrows; r += C::NTHR) {
-    const int ci = p.row_coef[it.row0 + r];
-    cbuf[r] = (ci >= 0 && !p.init_mode) ? make_float2(p.c_r[ci], p.c_i[ci]) : make_float2(0.f, 0.f);
+  // Rows past the item's last row are zero in both tile buffers (the bulk copies never touch them) and
+  // carry zero coefficients, so every warp that owns at least one row runs all RPT steps unguarded.
+  {
+    const int tail4 = (C::KMAX - it.nrows) * FT / 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = tid; e < tail4; e += C::NTHR) {
+      reinterpret_cast<float4*>(Abuf + it.nrows * FT)[e] = zero4;
+      reinterpret_cast<float4*>(Abuf + C::TILE_FLOATS + it.nrows * FT)[e] = zero4;
+    }
+  }
+  for (int r = tid; r < C::KMAX; r += C::NTHR) {
+    float2 c = make_float2(0.f, 0.f);
+    if (r < it.nrows && !p.init_mode) {
+      const int ci = p.row_coef[it.row0 + r];
+      if (ci >= 0) c = make_float2(p.c_r[ci], p.c_i[ci]);
+    }
+    cbuf[r] = c;
   }
   for (int s = tid; s < nsteps; s += C::NTHR) step_slot[s] = p.row_slot[it.row0 + s * G];
   for (int s = tid; s <= it.nslots; s += C::NTHR) {
@@ -210,30 +224,57 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
   }
   __syncthreads();
 
+  // warp-uniform description of this warp's RPT steps: first slot and a bit per step that starts a new slot
+  const int step_base = warp * RPT;
+  const bool warp_active = step_base < nsteps;
+  int s_first = 0;
+  unsigned chg = 0u;
+  if (warp_active) {
+    s_first = step_slot[step_base];
+    int prev = s_first;
+#pragma unroll
+    for (int i = 1; i < RPT; ++i) {
+      if (step_base + i < nsteps) {
+        const int s = step_slot[step_base + i];
+        if (s != prev) chg |= 1u << i;
+        prev = s;
+      }
+    }
+  }
+
   // Q-phase inputs of the first baseline of each (slot, channel) element this thread owns are prefetched
   // into registers one tile ahead: issued right after Q(j) for tile j + 1, so their DRAM/L2 latency is
   // covered by phase B, the tile wait and phase F instead of being exposed in every tile.
   constexpr int EPT = (C::SMAX * FT + C::NTHR - 1) / C::NTHR;
   float pf[EPT][7];
+  int qoff[EPT], qoff0[EPT], qoff1[EPT];  // element offsets at tile 0 (data row, ant0 row, ant1 row)
+#pragma unroll
+  for (int m = 0; m < EPT; ++m) {
+    const int e = tid + m * C::NTHR;
+    qoff[m] = -1;
+    qoff0[m] = qoff1[m] = 0;
+    if (e < it.nslots * FT) {
+      const int s = e / FT, f = e % FT;
+      const int b = slot_bl0[s];
+      if (b < slot_bl0[s + 1]) {
+        qoff[m] = b * p.nfp + f;
+        qoff0[m] = p.bl_ant0[b] * p.nfp + f;
+        qoff1[m] = p.bl_ant1[b] * p.nfp + f;
+      }
+    }
+  }
   auto prefetch_q = [&](int jt) {
 #pragma unroll
     for (int m = 0; m < EPT; ++m) {
-      const int e = tid + m * C::NTHR;
-      if (e < it.nslots * FT) {
-        const int s = e / FT, f = e % FT;
-        const int b = slot_bl0[s];
-        if (b < slot_bl0[s + 1]) {
-          const int fg = jt * FT + f;
-          const size_t o = (size_t)b * p.nfp + fg;
-          pf[m][0] = p.d_r[o];
-          pf[m][1] = p.d_i[o];
-          pf[m][2] = p.w[o];
-          const size_t o0 = (size_t)p.bl_ant0[b] * p.nfp + fg, o1 = (size_t)p.bl_ant1[b] * p.nfp + fg;
-          pf[m][3] = g_r[o0];
-          pf[m][4] = g_i[o0];
-          pf[m][5] = g_r[o1];
-          pf[m][6] = g_i[o1];
-        }
+      if (qoff[m] >= 0) {
+        const int o = qoff[m] + jt * FT, o0 = qoff0[m] + jt * FT, o1 = qoff1[m] + jt * FT;
+        pf[m][0] = p.d_r[o];
+        pf[m][1] = p.d_i[o];
+        pf[m][2] = p.w[o];
+        pf[m][3] = g_r[o0];
+        pf[m][4] = g_i[o0];
+        pf[m][5] = g_r[o1];
+        pf[m][6] = g_i[o1];
       }
     }
   };
@@ -245,6 +286,7 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[i][q] = 0.f;
   float loss_acc = 0.f, sr_acc = 0.f, si_acc = 0.f;
+  const int row_off = (step_base * G + usub) * FT + fl * 4;  // this thread's float offset of step 0 in a tile
 
   for (int j = 0; j < p.ntiles; ++j) {
     const int buf = j & 1;
@@ -253,12 +295,12 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
       bulk_g2s(Abuf + (buf ^ 1) * C::TILE_FLOATS, Abase + (size_t)(j + 1) * it.nrows * FT, tile_bytes, &mbar[buf ^ 1]);
     }
     mbar_wait(&mbar[buf], (j >> 1) & 1);
-    const float* Ab = Abuf + buf * C::TILE_FLOATS;
+    const float* Ab = Abuf + buf * C::TILE_FLOATS + row_off;
+    const float2* cb = cbuf + step_base * G + usub;
 
     // ---------------- phase F: forward contraction, partial per (warp, slot) ----------------
-    {
+    if (warp_active) {
       float4 vr = make_float4(0.f, 0.f, 0.f, 0.f), vi = vr;
-      int cur = -1;
       auto flush = [&](int seg) {
 #pragma unroll
         for (int off = FL; off < 32; off <<= 1) {
@@ -276,25 +318,32 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
           *reinterpret_cast<float4*>(vpart + (seg * 2 + 1) * FT + fl * 4) = vi;
         }
       };
+      if (chg == 0u) {  // all of this warp's rows belong to one slot: branch-free stream
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int stp = warp * RPT + i;
-        if (stp < nsteps) {  // warp-uniform
-          const int s = step_slot[stp];
-          if (s != cur) {
-            if (cur >= 0) flush(warp + cur);
-            vr = make_float4(0.f, 0.f, 0.f, 0.f);
-            vi = vr;
-            cur = s;
-          }
-          const int r = stp * G + usub;
-          const float4 a = *reinterpret_cast<const float4*>(Ab + r * FT + fl * 4);
-          const float2 c = cbuf[r];
+        for (int i = 0; i < RPT; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(Ab + i * G * FT);
+          const float2 c = cb[i * G];
           axpy4(c.x, a, vr);
           axpy4(c.y, a, vi);
         }
+        flush(warp + s_first);
+      } else {
+        int cur = s_first;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          if (i > 0 && ((chg >> i) & 1u)) {
+            flush(warp + cur);
+            vr = make_float4(0.f, 0.f, 0.f, 0.f);
+            vi = vr;
+            ++cur;
+          }
+          const float4 a = *reinterpret_cast<const float4*>(Ab + i * G * FT);
+          const float2 c = cb[i * G];
+          axpy4(c.x, a, vr);
+          axpy4(c.y, a, vi);
+        }
+        flush(warp + cur);
       }
-      if (cur >= 0) flush(warp + cur);
     }
     __syncthreads();
 
@@ -361,25 +410,34 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
     __syncthreads();
 
     // ---------------- phase B: backward contraction, accumulated in registers ----------------
-    {
+    if (warp_active) {
       float4 q0, q1, q2, q3;
-      int cur = -1;
+      auto load_q = [&](int s) {
+        q0 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 0) * FT + fl * 4);
+        q1 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 1) * FT + fl * 4);
+        if (SUM) {
+          q2 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 2) * FT + fl * 4);
+          q3 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 3) * FT + fl * 4);
+        }
+      };
+      load_q(s_first);
+      if (chg == 0u) {
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int stp = warp * RPT + i;
-        if (stp < nsteps) {
-          const int s = step_slot[stp];
-          if (s != cur) {
-            q0 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 0) * FT + fl * 4);
-            q1 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 1) * FT + fl * 4);
-            if (SUM) {
-              q2 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 2) * FT + fl * 4);
-              q3 = *reinterpret_cast<const float4*>(qbuf + (s * NQ + 3) * FT + fl * 4);
-            }
-            cur = s;
+        for (int i = 0; i < RPT; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(Ab + i * G * FT);
+          acc[i][0] = dot4(a, q0, acc[i][0]);
+          acc[i][1] = dot4(a, q1, acc[i][1]);
+          if (SUM) {
+            acc[i][2] = dot4(a, q2, acc[i][2]);
+            acc[i][3] = dot4(a, q3, acc[i][3]);
           }
-          const int r = stp * G + usub;
-          const float4 a = *reinterpret_cast<const float4*>(Ab + r * FT + fl * 4);
+        }
+      } else {
+        int cur = s_first;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          if (i > 0 && ((chg >> i) & 1u)) load_q(++cur);
+          const float4 a = *reinterpret_cast<const float4*>(Ab + i * G * FT);
           acc[i][0] = dot4(a, q0, acc[i][0]);
           acc[i][1] = dot4(a, q1, acc[i][1]);
           if (SUM) {
@@ -402,7 +460,7 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
       for (int off = 1; off < FL; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
       acc[i][q] = v;
     }
-    const int stp = warp * RPT + i;
+    const int stp = step_base + i;
     if (stp < nsteps && fl == 0) {
       float* dst = p.dcpart + (size_t)(it.row0 + stp * G + usub) * NQ;
       if (SUM)
