@@ -152,3 +152,135 @@ def yield_pbl_dpss_model_comps(
             eigenval_cutoff=eigenval_cutoff,
         )
     return out
+
+
+def get_uv_overlapping_grps_conjugated(
+    uvdata,
+    red_tol=1.0,
+    include_autos=False,
+    red_tol_freq=0.5,
+    n_angle_bins=200,
+    notebook_progressbar=False,
+    require_exact_angle_match=True,
+    angle_match_tol=1e-3,
+):
+    """Fitting groups = sets of redundant groups whose uv tracks come within `red_tol_freq` wavelengths of each
+    other somewhere in the band (modeling.py:84-252).
+
+    Returns fitting_grps (list of lists of redundant-group tuples), fitting_vec_centers, connections, grp_labels.
+    The traversal order (angle bins, (angle, length) sort, set iteration over connections) follows the reference
+    step for step because it defines the group ordering the golden vector of test_modeling.py:24-32 pins.
+    """
+    _, red_grps, centers, _ = get_redundant_grps_data(uvdata, include_autos=include_autos, tol=red_tol,
+                                                      remove_redundancy=False)
+    freqs = np.asarray(uvdata.freq_array[0])
+    fmin, fmax = uvdata.freq_array.min(), uvdata.freq_array.max()
+    center_of = {}
+    connections = {}
+    bins = {n: [] for n in range(n_angle_bins)}
+    dangle = np.pi / n_angle_bins
+    for gnum, (grp, vec) in enumerate(zip(red_grps, centers)):
+        center_of[tuple(grp)] = vec
+        if np.abs(vec[0]) > 0.0:
+            which = int(np.min([np.round((np.arctan(vec[1] / vec[0]) + np.pi / 2) / dangle), n_angle_bins - 2]))
+        else:
+            which = n_angle_bins - 1
+        bins[which].append(gnum)
+
+    def track_overlap(lo0, hi0, lo1, hi1):
+        return (lo0 > lo1 and lo0 < hi1) or (lo1 > lo0 and lo1 < hi0)
+
+    for which in PBARS[notebook_progressbar](range(n_angle_bins)):
+        members = bins[which]
+        for a, g0 in enumerate(members):
+            vec0 = centers[g0]
+            key0 = tuple(red_grps[g0])
+            if key0 not in connections:
+                connections[key0] = set({})
+                center_of[key0] = vec0
+            for g1 in members[a + 1 :]:
+                vec1 = centers[g1]
+                len0, len1 = np.linalg.norm(vec0), np.linalg.norm(vec1)
+                if not track_overlap(fmin * len0 / 3e8, fmax * len0 / 3e8, fmin * len1 / 3e8, fmax * len1 / 3e8):
+                    continue
+                if require_exact_angle_match and not (
+                    np.abs(np.arctan(vec0[1] / vec0[0]) - np.arctan(vec1[1] / vec1[0])) <= angle_match_tol
+                ):
+                    continue
+                u0, v0 = vec0[0] * freqs / 3e8, vec0[1] * freqs / 3e8
+                u1, v1 = vec1[0] * freqs / 3e8, vec1[1] * freqs / 3e8
+                du_m, dv_m = u0[None, :] - u1[:, None], v0[None, :] - v1[:, None]
+                du_p, dv_p = u0[None, :] + u1[:, None], v0[None, :] + v1[:, None]
+                if np.any(np.sqrt(np.abs(du_m) ** 2.0 + dv_m ** 2.0) <= red_tol_freq):
+                    key1 = tuple(red_grps[g1])
+                elif np.any(np.sqrt(np.abs(du_p) ** 2.0 + dv_p ** 2.0) <= red_tol_freq):
+                    # the second group overlaps once conjugated: flip it for everything that follows
+                    red_grps[g1] = [ap[::-1] for ap in red_grps[g1]]
+                    centers[g1] = [-c for c in centers[g1]]
+                    key1 = tuple(red_grps[g1])
+                else:
+                    continue
+                connections[key0].add(key1)
+                if key1 not in connections:
+                    connections[key1] = set({})
+                    center_of[key1] = vec1
+                connections[key1].add(key0)
+
+    keys = [k for k in center_of if k in connections]
+    lengths = [np.linalg.norm(center_of[k]) for k in keys]
+    angles = [np.arccos(center_of[k][0] / ln) for k, ln in zip(keys, lengths)]
+    order = sorted(range(len(keys)), key=lambda n: (angles[n], lengths[n]))
+    fitting = {}
+    grp_labels = {}
+    for n in PBARS[notebook_progressbar](order):
+        grp = keys[n]
+        if grp not in grp_labels:
+            fitting[grp] = [grp]
+            grp_labels[grp] = grp
+            parent = grp
+        else:
+            parent = grp_labels[grp]
+        for other in connections[grp]:
+            if other not in grp_labels:
+                fitting[parent].append(other)
+                grp_labels[other] = parent
+    fitting_grps = list(fitting.values())
+    fitting_vec_centers = [[center_of[grp] for grp in fit] for fit in fitting_grps]
+    return fitting_grps, fitting_vec_centers, connections, grp_labels
+
+
+def yield_mixed_comps(
+    fitting_grps,
+    fitting_blvecs,
+    freqs,
+    eigenval_cutoff=1e-10,
+    ant_dly=0.0,
+    horizon=1.0,
+    offset=0.0,
+    min_dly=0.0,
+    verbose=False,
+    dtype=np.float64,
+    notebook_progressbar=False,
+    use_tensorflow=False,
+    grp_size_threshold=5,
+):
+    """DPSS vectors for fitting groups of at most `grp_size_threshold` redundant groups (one dict entry per
+    redundant group, delay offset = ant_dly, as upstream), joint covariance eigenvectors keyed by the whole
+    fitting group otherwise (modeling.py:377-474)."""
+    from . import simple_cov
+
+    cache = {}
+    out = {}
+    for n in PBARS[notebook_progressbar](range(len(fitting_grps))):
+        fit = tuple(fitting_grps[n]) if isinstance(fitting_grps[n], list) else fitting_grps[n]
+        vecs = fitting_blvecs[n]
+        if len(fit) <= grp_size_threshold:
+            for red, ln in zip(fit, np.linalg.norm(vecs, axis=1)):
+                out[(red,)] = yield_dpss_model_comps_bl_grp(freqs=freqs, length=ln, offset=ant_dly, horizon=horizon,
+                                                            min_dly=min_dly, operator_cache=cache,
+                                                            eigenval_cutoff=eigenval_cutoff)
+        else:
+            out[fit] = simple_cov.yield_simple_multi_baseline_model_comps(
+                blvecs=vecs, ant_dly=ant_dly, offset=offset, min_dly=min_dly, horizon=horizon, dtype=dtype, freqs=freqs,
+                eigenval_cutoff=eigenval_cutoff, use_tensorflow=use_tensorflow, verbose=verbose)
+    return out

@@ -1,0 +1,253 @@
+"""CPU: host-side logic of the drop-in layer -- chunking / tensor layout / index construction (bit-exact
+against the oracle), the modeling golden vector of the reference, argparse defaults, sharding."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from calamity_b200 import calibration, modeling, simple_cov
+from calamity_b200.layout import RaggedLayout
+from calamity_b200.sharding import make_shard, partition_groups
+from calamity_b200.uvstandins import MiniUVData
+from oracle import restatement as R
+from tests import fixtures_uv as fx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol(native_built):
+    header = open(os.path.join(ROOT, "include", "calamity_b200.h")).read()
+    declared = set(re.findall(r"\b(calb2_[a-z0-9_]+)\s*\(", header))
+    from calamity_b200 import _native
+
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(native_built, sym)
+    assert b"sm_100a" in native_built.calb2_version()
+
+
+def test_get_uv_overlapping_grps_conjugated_golden():
+    """The one bit-exact vector in the reference's tests: calamity/tests/test_modeling.py:20-32."""
+    uvd = fx.line_array()
+    grps, centers, connections, labels = modeling.get_uv_overlapping_grps_conjugated(uvdata=uvd, red_tol_freq=0.5, n_angle_bins=200)
+    assert grps == [
+        [((0, 1),)],
+        [((3, 4),)],
+        [((1, 2),)],
+        [((0, 2),)],
+        [((4, 5),)],
+        [((2, 3),), ((3, 5),), ((2, 4),), ((1, 3),), ((0, 3),), ((1, 4),), ((0, 4),), ((2, 5),)],
+        [((1, 5),), ((0, 5),)],
+    ]
+
+
+@pytest.mark.parametrize("horizon, offset, min_dly, ant_dly", [(1.0, 20.0, 0.0, 0.0), (0.8, 123.0, 200.0, 0.0), (1.0, 0.0, 0.0, 2 / 0.3)])
+def test_simple_cov_closed_form(horizon, offset, min_dly, ant_dly):
+    """calamity/tests/test_simple_cov.py:21-45."""
+    freqs = 100e6 + 100e3 * np.arange(200)
+    blvecs = np.array([[2.0, 0.0, 0.0]])
+    fg0, fg1 = np.meshgrid(freqs, freqs)
+    bldly = np.max([np.linalg.norm(blvecs[0]) * horizon / 0.3 + offset, min_dly])
+    want = np.sinc(2 * bldly * (fg0 - fg1) / 1e9)
+    if ant_dly > 0:
+        want *= np.sinc(2 * (fg0 - fg1) / 1e9 * ant_dly)
+    got = simple_cov.simple_cov_matrix(blvecs, freqs, ant_dly=ant_dly, horizon=horizon, offset=offset, min_dly=min_dly)
+    assert np.allclose(got, want)
+
+
+def test_dpss_fit_argparser_defaults():
+    """calamity/tests/test_calibration.py:758-765."""
+    argv = sys.argv
+    sys.argv = [argv[0], "--input_data_files", "input.uvh5"]
+    try:
+        args = calibration.dpss_fit_argparser().parse_args()
+    finally:
+        sys.argv = argv
+    assert args.learning_rate == 1e-2 and args.tol == 1e-14 and args.maxsteps == 10000
+    assert args.input_data_files == ["input.uvh5"]
+    assert args.model_regularization == "post_hoc" and args.optimizer == "Adamax" and args.precision == 32
+
+
+def _mixed_dict(nfreqs=24, seed=0):
+    rng = np.random.default_rng(seed)
+    d = {}
+    d[(((0, 1), (1, 2)), ((0, 2),))] = rng.standard_normal((2 * nfreqs, 5))        # unequal sub-group sizes: never split
+    d[(((2, 3), (3, 4)), ((1, 3), (2, 4)))] = rng.standard_normal((2 * nfreqs, 7))  # equal sizes: split unless use_redundancy
+    d[(((0, 4),),)] = rng.standard_normal((nfreqs, 3))
+    d[(((0, 3),), ((1, 4),), ((0, 5),), ((1, 5),), ((2, 5),), ((3, 5),))] = rng.standard_normal((6 * nfreqs, 9))  # too many to split
+    d[(((4, 5),),)] = rng.standard_normal((nfreqs, 4))
+    return d, nfreqs
+
+
+@pytest.mark.parametrize("use_redundancy", [False, True])
+@pytest.mark.parametrize("threshold", [1, 3, 5, 7])
+def test_chunking_and_tensor_layout_match_oracle_bit_exact(use_redundancy, threshold):
+    d, nf = _mixed_dict()
+    ants_map = {a: a for a in range(6)}
+    mine = calibration.chunk_fg_comp_dict_by_nbls(d, use_redundancy=use_redundancy, grp_size_threshold=threshold)
+    want = R.chunk_by_nbls(d, use_redundancy=use_redundancy, grp_size_threshold=threshold)
+    assert list(mine.keys()) == list(want.keys())
+    for k in want:
+        assert list(mine[k].keys()) == list(want[k].keys())
+    dense, corr = calibration.tensorize_fg_model_comps_dict(d, ants_map, nf, use_redundancy=use_redundancy,
+                                                            dtype=np.float64, grp_size_threshold=threshold)
+    odense, ocorr = R.tensorize_basis(d, ants_map, nf, use_redundancy=use_redundancy, dtype=np.float64,
+                                      grp_size_threshold=threshold)
+    assert corr == ocorr
+    assert len(dense) == len(odense)
+    for a, b in zip(dense, odense):
+        assert a.dtype == np.float64 and np.array_equal(a.numpy(), b)
+    # the ragged layout carries the same information as the dense tensors
+    lay = calibration._layout_from_dict(d, ants_map, nf, use_redundancy, threshold)
+    for a, b in zip(lay.dense_chunks(np.float32), odense):
+        assert np.array_equal(a, b.astype(np.float32))
+    assert lay.corr_inds() == ocorr
+    assert sum(t.shape[1] * t.shape[2] * t.shape[3] for t in dense) == lay.nbls * nf
+    # dense -> ragged -> dense is lossless, and flat <-> chunked vectors round-trip
+    lay2 = RaggedLayout.from_dense([b.astype(np.float32) for b in odense], ocorr, 6)
+    for a, b in zip(lay2.dense_chunks(np.float32), odense):
+        assert np.array_equal(a, b.astype(np.float32))
+    rng = np.random.default_rng(1)
+    flat = rng.standard_normal(lay.ncoef).astype(np.float32)
+    assert np.array_equal(lay.flatten_coeffs(lay.unflatten_coeffs(flat)), flat)
+    data = rng.standard_normal((lay.nbls, nf)).astype(np.float32)
+    assert np.array_equal(lay.flatten_data(lay.unflatten_data(data)), data)
+
+
+def test_chunk_dpss_dict_is_one_chunk():
+    """calamity/tests/test_calibration.py:274-278."""
+    comps = fx.dpss_vectors(fx.line_array())
+    chunked = calibration.chunk_fg_comp_dict_by_nbls(comps)
+    maxvecs = np.max([comps[k].shape[1] for k in comps])
+    assert len(chunked) == 1 and list(chunked.keys())[0] == (1, maxvecs)
+
+
+def test_tensorize_fg_model_comps_dpss_rows_and_padding():
+    """calamity/tests/test_calibration.py:244-271."""
+    uvd = fx.line_array()
+    comps = fx.dpss_vectors(uvd)
+    gains = fx.cal_utils.blank_uvcal_from_uvdata(uvd)
+    ants_map = {ant: i for i, ant in enumerate(gains.ant_array)}
+    tensors, corr = calibration.tensorize_fg_model_comps_dict(comps, ants_map, dtype=np.float64, nfreqs=uvd.Nfreqs)
+    seen = 0
+    for c in range(len(corr)):
+        for g in range(len(corr[c])):
+            for b, bl in enumerate(corr[c][g]):
+                rows = tensors[c][:, g, b].numpy().squeeze()
+                want = comps[((bl,),)].T
+                assert np.allclose(want, rows[: want.shape[0]])
+                assert np.allclose(0.0, rows[want.shape[0] :])
+                seen += 1
+    assert seen == len(comps)
+
+
+def test_tensorize_gains_layout():
+    """calamity/tests/test_calibration.py:233-241."""
+    uvd = fx.line_array()
+    gains = fx.cal_utils.blank_uvcal_from_uvdata(uvd)
+    for i, ant in enumerate(gains.ant_array):
+        gains.gain_array[i] *= ant + 1.0
+    g_r, g_i = calibration.tensorize_gains(gains, polarization="xx", time=gains.time_array[0], dtype=np.float64)
+    assert g_r.dtype == np.float64 and g_i.dtype == np.float64
+    for ant in gains.ant_array:
+        assert np.allclose(g_r.numpy()[ant], ant + 1) and np.allclose(g_i.numpy()[ant], 0.0)
+
+
+def test_tensorize_data_matches_oracle_and_handles_conjugates():
+    uvd = fx.line_array()
+    rng = np.random.default_rng(3)
+    uvd.flag_array[:] = rng.random(uvd.flag_array.shape) < 0.1
+    uvd.nsample_array[:] = rng.integers(1, 4, uvd.nsample_array.shape)
+    gains = fx.cal_utils.blank_uvcal_from_uvdata(uvd)
+    ants_map = {ant: i for i, ant in enumerate(gains.ant_array)}
+    # ask for some baselines in the orientation the data does NOT store: they must come back conjugated
+    comps = {}
+    for n, ap in enumerate(uvd.get_antpairs()):
+        key = ap if n % 2 == 0 else ap[::-1]
+        comps[((key,),)] = np.ones((uvd.Nfreqs, 2))
+    _, corr = calibration.tensorize_fg_model_comps_dict(comps, ants_map, uvd.Nfreqs)
+    before = uvd.data_array.copy()
+    d_r, d_i, w = calibration.tensorize_data(uvd, corr, ants_map, "xx", uvd.time_array[0], data_scale_factor=3.0,
+                                             nsamples_in_weights=True, dtype=np.float64)
+    assert np.array_equal(before, uvd.data_array)  # the caller's data are not rescaled in place
+    n = uvd.Nants_data
+    cube = np.zeros((n, n, uvd.Nfreqs), dtype=np.complex128)
+    flg = np.ones((n, n, uvd.Nfreqs), dtype=bool)
+    ns = np.zeros((n, n, uvd.Nfreqs))
+    for ap in uvd.get_antpairs():
+        row = uvd.antpair2ind(ap)[0]
+        i, j = ants_map[ap[0]], ants_map[ap[1]]
+        cube[i, j] = uvd.data_array[row, 0, :, 0]
+        cube[j, i] = np.conj(uvd.data_array[row, 0, :, 0])
+        flg[i, j] = flg[j, i] = uvd.flag_array[row, 0, :, 0]
+        ns[i, j] = ns[j, i] = uvd.nsample_array[row, 0, :, 0]
+    o_r, o_i, o_w = R.tensorize_data_cubes(cube, flg, ns, corr, data_scale_factor=3.0, nsamples_in_weights=True, dtype=np.float64)
+    for a, b in zip(d_r + d_i + w, o_r + o_i + o_w):
+        assert np.array_equal(a.numpy(), b)
+    assert abs(sum(float(x.numpy().sum()) for x in w) - 1.0) < 1e-12
+    with pytest.raises(IndexError):
+        calibration.tensorize_data(uvd, corr, ants_map, "xx", uvd.time_array[0] + 1.0)
+
+
+def test_flag_poltime_and_renormalize():
+    """calamity/tests/test_calibration.py:222-230, 599-607."""
+    uvd = fx.line_array(ntimes=2)
+    ref = fx.copy.deepcopy(uvd)
+    t0 = np.unique(uvd.time_array)[0]
+    calibration.flag_poltime(uvd, time=t0, polarization="xx")
+    assert np.all(uvd.flag_array[: uvd.Nbls]) and not np.any(uvd.flag_array[uvd.Nbls : 2 * uvd.Nbls])
+    assert np.allclose(uvd.data_array[: uvd.Nbls], 0.0)
+    assert np.allclose(uvd.data_array[uvd.Nbls :], ref.data_array[uvd.Nbls :])
+    gains = fx.cal_utils.blank_uvcal_from_uvdata(ref)
+    gains.gain_array *= 3.0
+    calibration.flag_poltime(gains, time=t0, polarization="xx")
+    assert np.allclose(gains.gain_array[:, 0, :, 0, 0], 1.0) and np.all(gains.flag_array[:, 0, :, 0, 0])
+    assert np.allclose(gains.gain_array[:, 0, :, 1, 0], 3.0)
+    with pytest.raises(ValueError):
+        calibration.flag_poltime(data_object="blarghle", time=0, polarization="xx")
+    sky = fx.line_array()
+    sky_ref = fx.copy.deepcopy(sky)
+    g = fx.cal_utils.blank_uvcal_from_uvdata(sky)
+    g.gain_array *= (51.0 + 23j) ** -0.5
+    sky.data_array *= 51.0 + 23j
+    calibration.renormalize(sky_ref, sky, g, polarization="xx", time=sky.time_array[0])
+    assert np.allclose(np.abs(g.gain_array), 1.0)
+    assert np.allclose(np.abs(sky_ref.data_array), np.abs(sky.data_array))
+
+
+def test_insert_gains_and_apply_gains_roundtrip():
+    uvd = fx.line_array()
+    gains = fx.randomized_gains(uvd, scatter=0.1)
+    cal = fx.cal_utils.apply_gains(uvd, gains)
+    back = fx.cal_utils.apply_gains(cal, gains, inverse=True)
+    assert np.allclose(back.data_array, uvd.data_array)
+    ap = uvd.get_antpairs()[3]
+    row = uvd.antpair2ind(ap)[0]
+    i0 = np.where(gains.ant_array == ap[0])[0][0]
+    i1 = np.where(gains.ant_array == ap[1])[0][0]
+    want = uvd.data_array[row, 0, :, 0] / (gains.gain_array[i0, 0, :, 0, 0] * np.conj(gains.gain_array[i1, 0, :, 0, 0]))
+    assert np.allclose(cal.data_array[row, 0, :, 0], want)
+    g2 = fx.cal_utils.blank_uvcal_from_uvdata(uvd)
+    rng = np.random.default_rng(0)
+    gr, gi = rng.standard_normal((6, 200)), rng.standard_normal((6, 200))
+    calibration.insert_gains_into_uvcal(g2, uvd.time_array[0], "xx", gr, gi)
+    assert np.allclose(g2.gain_array[:, 0, :, 0, 0], gr + 1j * gi)
+
+
+def test_partition_balances_bytes_not_counts():
+    w = np.concatenate([np.full(100, 5), np.full(20, 200)])
+    for n in (2, 4, 8):
+        ranges = partition_groups(w, n)
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(w)
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        loads = np.array([w[a:b].sum() for a, b in ranges])
+        assert loads.max() <= w.sum() / n + w.max()
+
+
+def test_unknown_optimizer_is_a_keyerror(native_built):
+    from calamity_b200.fitter import FitPlan
+
+    with pytest.raises(KeyError):
+        FitPlan.fit(None, optimizer="NotAnOptimizer")
