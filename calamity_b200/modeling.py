@@ -93,32 +93,14 @@ def get_redundant_grps_data(uvdata, remove_redundancy=False, tol=1.0, include_au
 
 
 def _redundancies_from_positions(antpos, tol, include_autos):
-    ants = sorted(antpos)
-    vecs, pairs = [], []
-    for a, i in enumerate(ants):
-        for j in ants[a if include_autos else a + 1 :]:
-            vec = antpos[j] - antpos[i]
-            pair = (i, j)
-            # conjugate so that the baseline points to u > 0 (or v > 0 on the meridian)
-            if vec[0] < -tol or (abs(vec[0]) <= tol and vec[1] < -tol) or (
-                abs(vec[0]) <= tol and abs(vec[1]) <= tol and vec[2] < -tol
-            ):
-                vec, pair = -vec, (j, i)
-            vecs.append(vec)
-            pairs.append(pair)
-    groups, centers = [], []
-    for vec, pair in zip(vecs, pairs):
-        for n, c in enumerate(centers):
-            if np.linalg.norm(vec - c) <= tol:
-                groups[n].append(pair)
-                break
-        else:
-            groups.append([pair])
-            centers.append(np.array(vec))
-    centers = [np.mean([antpos[j] - antpos[i] for (i, j) in grp], axis=0) for grp in groups]
-    lengths = [float(np.linalg.norm(c)) for c in centers]
-    order = np.argsort(lengths, kind="stable")
-    return [groups[n] for n in order], [centers[n] for n in order], [lengths[n] for n in order]
+    """Fallback for objects without pyuvdata's `get_redundancies`: same grouping via the stand-in's finder."""
+    from .uvstandins import MiniUVData
+
+    probe = MiniUVData.__new__(MiniUVData)
+    probe.antpos = antpos
+    bl_groups, centers, lengths, _ = probe.get_redundancies(tol=tol, use_antpos=True, include_conjugates=True,
+                                                            include_autos=include_autos)
+    return [[MiniUVData.baseline_to_antnums(bl) for bl in grp] for grp in bl_groups], centers, lengths
 
 
 def yield_pbl_dpss_model_comps(

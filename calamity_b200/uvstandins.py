@@ -132,6 +132,48 @@ class MiniUVData:
         rows, p = (fwd, pidx[0]) if len(fwd) else (rev, pconj[0])
         return self.flag_array[rows, 0][:, :, p]
 
+    # ---- redundancy finder with pyuvdata's interface (groups of baseline numbers, conjugated to u > 0)
+    @staticmethod
+    def antnums_to_baseline(a, b):
+        return 2048 * (int(a) + 1) + (int(b) + 1) + 2 ** 16
+
+    @staticmethod
+    def baseline_to_antnums(bl):
+        bl = int(bl) - 2 ** 16
+        return (bl // 2048 - 1, bl % 2048 - 1)
+
+    def get_redundancies(self, tol=1.0, use_antpos=False, include_conjugates=False, include_autos=True, **kwargs):
+        ants = sorted(self.antpos)
+        vecs, pairs = [], []
+        for n, i in enumerate(ants):
+            for j in ants[n if include_autos else n + 1 :]:
+                vec = self.antpos[j] - self.antpos[i]
+                pair = (i, j)
+                flip = vec[0] < -tol or (abs(vec[0]) <= tol and vec[1] < -tol) or (
+                    abs(vec[0]) <= tol and abs(vec[1]) <= tol and vec[2] < -tol)
+                if include_conjugates and flip:
+                    vec, pair = -vec, (j, i)
+                vecs.append(vec)
+                pairs.append(pair)
+        groups, seeds = [], []
+        for vec, pair in zip(vecs, pairs):
+            for n, c in enumerate(seeds):
+                if np.linalg.norm(vec - c) <= tol:
+                    groups[n].append(pair)
+                    break
+            else:
+                groups.append([pair])
+                seeds.append(np.array(vec))
+        centers = [np.mean([self.antpos[j] - self.antpos[i] for (i, j) in grp], axis=0) for grp in groups]
+        lengths = [float(np.linalg.norm(c)) for c in centers]
+        order = np.argsort(lengths, kind="stable")
+        bl_groups = [[self.antnums_to_baseline(*ap) for ap in groups[n]] for n in order]
+        return bl_groups, [centers[n] for n in order], [lengths[n] for n in order], []
+
+    @property
+    def uvw_array(self):
+        return np.asarray([self.antpos[b] - self.antpos[a] for a, b in zip(self.ant_1_array.tolist(), self.ant_2_array.tolist())])
+
     def select(self, bls=None, times=None, inplace=True):
         obj = self if inplace else copy.deepcopy(self)
         keep = np.ones(obj.Nblts, dtype=bool)
