@@ -298,6 +298,14 @@ def main():
         # data_i / weights once, coefficients once (DESIGN.md "Roofline accounting"); whole-iteration figure is B_iter.
         sh = shard.layout.sizes()
         heavy_bytes = 4 * sh["n_a_nz"] + 12 * sh["n_d"] + 8 * sh["n_c_nz"]
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "heavy_traffic.json")) as f:
+                tr = json.load(f).get(args.workload)
+            if tr and world == 1 and args.reg != "sum":
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         heavy_avg_ms = heavy_ms / args.steps
         achieved = heavy_bytes / (heavy_avg_ms * 1e-3) / 1e9 if heavy_avg_ms > 0 else None
         iter_gbs = sizes["b_iter"] / (loop_ms / args.steps * 1e-3) / 1e9 / world
@@ -315,7 +323,7 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": f"heavy_kernel<FL={info['tile_freqs'] // 4},SUM={int(reg == 'sum')}>",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": heavy_bytes,
+                "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": heavy_bytes,
                 "avg_launch_ms": heavy_avg_ms, "kernel_share_of_step": heavy_ms / loop_ms if loop_ms > 0 else None,
                 "iteration": {"b_iter_bytes": sizes["b_iter"], "per_gpu_gbs": iter_gbs, "frac": iter_gbs / peak},
             },
