@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--reg", default="post_hoc", choices=["post_hoc", "sum"])
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--graph", type=int, default=0)
+    ap.add_argument("--fuse", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-bls", type=int, default=384)
     ap.add_argument("--cpu-steps", type=int, default=6)
@@ -238,7 +239,7 @@ def main():
         pr = float(np.sum(prob.data_r.astype(np.float64) * prob.wgts))
         pi = float(np.sum(prob.data_i.astype(np.float64) * prob.wgts))
     fit_kw = dict(optimizer="Adamax", tol=0.0, learning_rate=1e-2, model_regularization=reg, prior_r_sum=pr,
-                  prior_i_sum=pi, use_graph=bool(args.graph), steps_per_sync=max(args.steps, args.warmup) + 1)
+                  prior_i_sum=pi, use_graph=bool(args.graph), fuse_tail_update=bool(args.fuse), steps_per_sync=max(args.steps, args.warmup) + 1)
 
     def load_inputs():
         plan.set_integration(d_r, d_i, w)

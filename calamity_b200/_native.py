@@ -48,6 +48,7 @@ class FitOptions(C.Structure):
         ("n_profile_steps", C.c_int32),
         ("steps_per_sync", C.c_int32),
         ("use_graph", C.c_int32),
+        ("fuse_tail_update", C.c_int32),
     ]
 
 

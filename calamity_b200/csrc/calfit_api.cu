@@ -124,7 +124,9 @@ struct calb2_plan {
   FitState* h_state = nullptr;  // pinned
   cudaStream_t stream = nullptr;
   int cur_buf = 0;
-  bool have_data = false, have_gains = false, have_coeffs = false, basis_complete = false;
+  bool have_data = false, have_gains = false, have_coeffs = false, basis_complete = false, all_single_slot = true;
+  int light_blocks = 0;
+  DevBuf<double> light_partials;
   long long basis_groups_set = 0;
   // comm
   void* comm = nullptr;
@@ -225,6 +227,13 @@ static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, in
   hp.ntiles = pl->ntiles;
   hp.store_v = store_v;
   hp.init_mode = init_mode;
+  hp.fuse_update = 0;
+  hp.c_r_rw = pl->c_r.p;
+  hp.c_i_rw = pl->c_i.p;
+  hp.cm_r = pl->cm_r.p;
+  hp.cu_r = pl->cu_r.p;
+  hp.cm_i = pl->cm_i.p;
+  hp.cu_i = pl->cu_i.p;
   return hp;
 }
 
@@ -358,11 +367,43 @@ static int all_reduce(calb2_plan* pl, void* buf, size_t count, int dtype) {
 }
 
 // One optimizer iteration (calibration.py:663-668) enqueued on the plan's stream.
-static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freeze, float* hist, cudaEvent_t ev0,
-                        cudaEvent_t ev1, long long* launches) {
-  HeavyParams hp = heavy_params(pl, pl->state.p, sum, 0, 0);
+static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freeze, bool want_fuse, float* hist,
+                        cudaEvent_t ev0, cudaEvent_t ev1, long long* launches) {
+  // coefficients can take their optimizer step in the heavy kernel's tail when nothing couples the groups
+  const bool fuse = want_fuse && !sum && !freeze && pl->all_single_slot;
+  int npartials = (int)pl->items.size();
+  const double* partials = pl->partials.p;
   if (ev0) CU(cudaEventRecord(ev0, pl->stream));
-  CU(launch_heavy(pl->FL, sum, hp, (int)pl->items.size(), pl->stream));
+  if (freeze) {  // the model is fixed: elementwise pass over the visibilities only
+    LightParams lp{};
+    lp.vout = pl->vout.p;
+    lp.bl_slot = pl->d_bl_slot.p;
+    lp.bl_ant0 = pl->d_bl_ant0.p;
+    lp.bl_ant1 = pl->d_bl_ant1.p;
+    lp.d_r = pl->d_r.p;
+    lp.d_i = pl->d_i.p;
+    lp.w = pl->w.p;
+    for (int b = 0; b < 2; ++b) {
+      lp.g_r[b] = pl->g_r[b].p;
+      lp.g_i[b] = pl->g_i[b].p;
+    }
+    lp.z = pl->z.p;
+    lp.y = sum ? pl->y.p : nullptr;
+    lp.partials = pl->light_partials.p;
+    lp.st = pl->state.p;
+    lp.nfp = pl->nfp;
+    lp.nelem = pl->nbls * (long long)pl->nfp;
+    lp.sum = sum ? 1 : 0;
+    light_kernel<<<pl->light_blocks, 256, 0, pl->stream>>>(lp);
+    CU(cudaGetLastError());
+    npartials = pl->light_blocks;
+    partials = pl->light_partials.p;
+  } else {
+    HeavyParams hp = heavy_params(pl, pl->state.p, sum, 0, 0);
+    hp.fuse_update = fuse ? 1 : 0;
+    hp.k = k;
+    CU(launch_heavy(pl->FL, sum, hp, (int)pl->items.size(), pl->stream));
+  }
   if (ev1) CU(cudaEventRecord(ev1, pl->stream));
   FinalizeParams fp{};
   fp.st = pl->state.p;
@@ -370,19 +411,19 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
   fp.hist = hist;
   fp.eval_only = 0;
   if (pl->nranks > 1) {
-    reduce_partials_kernel<<<1, 1024, 0, pl->stream>>>(pl->partials.p, (int)pl->items.size(), pl->comm_scalars.p);
+    reduce_partials_kernel<<<1, 1024, 0, pl->stream>>>(partials, npartials, pl->comm_scalars.p);
     CU(cudaGetLastError());
     if (int r = all_reduce(pl, pl->comm_scalars.p, 4, NCCL_FLOAT64)) return r;
     fp.partials = pl->comm_scalars.p;
     fp.nitems = 1;
     *launches += 1;
   } else {
-    fp.partials = pl->partials.p;
-    fp.nitems = (int)pl->items.size();
+    fp.partials = partials;
+    fp.nitems = npartials;
   }
   finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
   CU(cudaGetLastError());
-  dim3 ggrid((pl->nfp + 127) / 128, pl->nants);
+  dim3 ggrid((pl->nfp / 2 + 127) / 128, pl->nants);
   if (pl->nranks > 1) {
     gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 1, sum, 0));
     CU(cudaGetLastError());
@@ -395,9 +436,10 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 0, sum, 0));
     CU(cudaGetLastError());
   }
-  if (!freeze || k.use_min) {
+  if ((!freeze && !fuse) || (k.use_min && !freeze)) {
+    // mode 0: optimizer step from the stored backward sums; mode 3: only the use_min snapshot copy
     coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(
-        coeff_params(pl, pl->state.p, k, freeze ? 3 : 0, sum));
+        coeff_params(pl, pl->state.p, k, fuse ? 3 : 0, sum));
     CU(cudaGetLastError());
     *launches += 1;
   }
@@ -523,6 +565,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     }
     pl->grp_slot0[g] = (int)ns;
     pl->grp_coef0[g] = (int)nc;
+    if (d->group_nslots[g] != 1) pl->all_single_slot = false;
     ns += d->group_nslots[g];
     nc += d->group_ncomp[g];
   }
@@ -714,6 +757,7 @@ int calb2_plan_destroy(calb2_plan* pl) {
   pl->partials.release();
   pl->red_d.release();
   pl->comm_scalars.release();
+  pl->light_partials.release();
   pl->d_items.release();
   pl->row_slot.release();
   DevBuf<int>* ib[] = {&pl->row_coef, &pl->d_slot_row0, &pl->d_slot_bl0, &pl->d_bl_ant0, &pl->d_bl_ant1, &pl->d_bl_slot,
@@ -963,7 +1007,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, 
   fp.eval_only = 1;
   finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
   CU(cudaGetLastError());
-  dim3 ggrid((pl->nfp + 127) / 128, pl->nants);
+  dim3 ggrid((pl->nfp / 2 + 127) / 128, pl->nants);
   gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state_eval.p, k, 1, sum, 1));
   CU(cudaGetLastError());
   coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(coeff_params(pl, pl->state_eval.p, k, 1, sum));
@@ -1023,6 +1067,15 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
   if (pl->hist.n < (size_t)std::max(1, o->maxsteps)) {
     if (int r = dalloc(pl->hist, (size_t)std::max(1, o->maxsteps), pl)) return r;
   }
+  if (freeze) {
+    if (!pl->light_blocks) {
+      int nsm = 148;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, pl->device);
+      pl->light_blocks = nsm * 8;
+      if (int r = dalloc(pl->light_partials, (size_t)pl->light_blocks * 4, pl)) return r;
+    }
+    if (int r = run_forward_store_v(pl)) return r;  // v = sum_k c_k A_k, once: the coefficients are frozen
+  }
   FitState s0{};
   s0.step = 0;
   s0.stop_after = (int)(total - 1);
@@ -1047,7 +1100,7 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
   if (o->use_graph && pl->nranks == 1) {
     long long dummy = 0;
     CU(cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < chunk && !rc; ++i) rc = enqueue_step(pl, k, sum, freeze, pl->hist.p, nullptr, nullptr, &dummy);
+    for (int i = 0; i < chunk && !rc; ++i) rc = enqueue_step(pl, k, sum, freeze, o->fuse_tail_update != 0, pl->hist.p, nullptr, nullptr, &dummy);
     cudaError_t ce = cudaStreamEndCapture(pl->stream, &graph);
     if (rc) return rc;
     CU(ce);
@@ -1059,11 +1112,11 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
     const int n = (int)std::min<long long>(chunk, total - done);
     if (gexec) {
       CU(cudaGraphLaunch(gexec, pl->stream));
-      launches += (long long)chunk * (freeze && !k.use_min ? 3 : 4);
+      launches += (long long)chunk * 4;
       heavy_launches += chunk;
     } else {
       for (int i = 0; i < n; ++i) {
-        if (int r = enqueue_step(pl, k, sum, freeze, pl->hist.p, time_heavy ? evs[2 * i] : nullptr,
+        if (int r = enqueue_step(pl, k, sum, freeze, o->fuse_tail_update != 0, pl->hist.p, time_heavy ? evs[2 * i] : nullptr,
                                  time_heavy ? evs[2 * i + 1] : nullptr, &launches))
           return r;
         heavy_launches++;

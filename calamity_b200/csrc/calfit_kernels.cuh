@@ -82,6 +82,16 @@ struct HeavyParams {
   int ntiles;
   int store_v;
   int init_mode;                  // 1: dL/dv := data * (w != 0)   (right-hand side of the lstsq initialisation)
+  // fused tail update (every group single-slot, no regulariser coupling): the item's own coefficients take
+  // their optimizer step right after the backward sums are complete
+  int fuse_update;
+  float* c_r_rw;
+  float* c_i_rw;
+  float* cm_r;
+  float* cu_r;
+  float* cm_i;
+  float* cu_i;
+  FitConsts k;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -125,6 +135,37 @@ __device__ __forceinline__ void axpy4(float c, const float4& a, float4& v) {
   v.y = fmaf(c, a.y, v.y);
   v.z = fmaf(c, a.z, v.z);
   v.w = fmaf(c, a.w, v.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimizer rules (Keras OptimizerV2; see oracle/restatement.py for provenance)
+//   SPARSE = the IndexedSlices form used for the gains, dense form for the coefficients
+// ------------------------------------------------------------------------------------------------
+template <bool SPARSE>
+__device__ __forceinline__ float opt_step(int optimizer, float theta, float g, float& m, float& u, float lr_t,
+                                          float beta1, float beta2, float eps) {
+  if (optimizer == 0) {  // Adamax
+    m = SPARSE ? (m * beta1 + g * (1.f - beta1)) : (m + (g - m) * (1.f - beta1));
+    u = fmaxf(u * beta2, fabsf(g));
+    return theta - lr_t * (m / (u + eps));
+  } else if (optimizer == 1) {  // Adam
+    m = SPARSE ? (m * beta1 + g * (1.f - beta1)) : (m + (g - m) * (1.f - beta1));
+    u = SPARSE ? (u * beta2 + (g * g) * (1.f - beta2)) : (u + (g * g - u) * (1.f - beta2));
+    return theta - (m * lr_t) / (sqrtf(u) + eps);
+  }
+  return theta - lr_t * g;  // SGD without momentum
+}
+
+// Keras local_step = iterations + 1; powers evaluated in double and rounded once (identical in every kernel)
+__device__ __forceinline__ float bias_corrected_lr(const FitConsts& k, int step) {
+  const double tt = (double)(step + 1);
+  const float b1p = (float)pow((double)k.beta1, tt);
+  if (k.optimizer == 0) return k.lr / (1.f - b1p);
+  if (k.optimizer == 1) {
+    const float b2p = (float)pow((double)k.beta2, tt);
+    return k.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+  }
+  return k.lr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -451,6 +492,10 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
   }
 
   // ---------------- item epilogue: lane reduction of the backward sums ----------------
+  // The reduced sums are staged in shared memory (the tile buffers are free now) so that the write-out --
+  // or, in the fused case, the optimizer step on the item's own coefficients -- is done by all 256 threads
+  // with coalesced accesses instead of by one lane per row.
+  float* rowdc = Abuf;  // [nrows][NQ]
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
 #pragma unroll
@@ -462,12 +507,34 @@ __global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
     }
     const int stp = step_base + i;
     if (stp < nsteps && fl == 0) {
-      float* dst = p.dcpart + (size_t)(it.row0 + stp * G + usub) * NQ;
+      float* dst = rowdc + (stp * G + usub) * NQ;
       if (SUM)
         *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       else
         *reinterpret_cast<float2*>(dst) = make_float2(acc[i][0], acc[i][1]);
     }
+  }
+  __syncthreads();
+  if (!SUM && p.fuse_update) {
+    const float lr_fused = bias_corrected_lr(p.k, st->step);
+    for (int r = tid; r < it.nrows; r += C::NTHR) {
+      const int ci = p.row_coef[it.row0 + r];
+      if (ci >= 0) {
+        const float2 g = *reinterpret_cast<const float2*>(rowdc + r * 2);
+        float mr = p.cm_r[ci], ur = p.cu_r[ci], mi = p.cm_i[ci], ui = p.cu_i[ci];
+        const float nr = opt_step<false>(p.k.optimizer, p.c_r_rw[ci], g.x, mr, ur, lr_fused, p.k.beta1, p.k.beta2, p.k.eps);
+        const float ni = opt_step<false>(p.k.optimizer, p.c_i_rw[ci], g.y, mi, ui, lr_fused, p.k.beta1, p.k.beta2, p.k.eps);
+        p.cm_r[ci] = mr;
+        p.cu_r[ci] = ur;
+        p.cm_i[ci] = mi;
+        p.cu_i[ci] = ui;
+        p.c_r_rw[ci] = nr;
+        p.c_i_rw[ci] = ni;
+      }
+    }
+  } else {
+    float* dst = p.dcpart + (size_t)it.row0 * NQ;
+    for (int e = tid; e < it.nrows * NQ; e += C::NTHR) dst[e] = rowdc[e];
   }
 
   // ---------------- per-CTA partial sums (fixed order -> deterministic) ----------------
@@ -559,17 +626,7 @@ __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams 
   if (p.eval_only) return;
 
   const int t = st->step;
-  // Keras local_step = iterations + 1; powers evaluated in double and rounded once
-  const double tt = (double)(t + 1);
-  const float b1p = (float)pow((double)p.k.beta1, tt);
-  if (p.k.optimizer == 0) {
-    st->lr_t = p.k.lr / (1.f - b1p);
-  } else if (p.k.optimizer == 1) {
-    const float b2p = (float)pow((double)p.k.beta2, tt);
-    st->lr_t = p.k.lr * sqrtf(1.f - b2p) / (1.f - b1p);
-  } else {
-    st->lr_t = p.k.lr;
-  }
+  st->lr_t = bias_corrected_lr(p.k, t);
   int snap = 0;
   const int rec = t - p.k.n_skip;
   if (rec >= 0) {
@@ -587,25 +644,6 @@ __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams 
   st->snap = snap;
   st->upd_active = 1;
   st->step = t + 1;
-}
-
-// ------------------------------------------------------------------------------------------------
-// optimizer rules (Keras OptimizerV2; see oracle/restatement.py for provenance)
-//   SPARSE = the IndexedSlices form used for the gains, dense form for the coefficients
-// ------------------------------------------------------------------------------------------------
-template <bool SPARSE>
-__device__ __forceinline__ float opt_step(int optimizer, float theta, float g, float& m, float& u, float lr_t,
-                                          float beta1, float beta2, float eps) {
-  if (optimizer == 0) {  // Adamax
-    m = SPARSE ? (m * beta1 + g * (1.f - beta1)) : (m + (g - m) * (1.f - beta1));
-    u = fmaxf(u * beta2, fabsf(g));
-    return theta - lr_t * (m / (u + eps));
-  } else if (optimizer == 1) {  // Adam
-    m = SPARSE ? (m * beta1 + g * (1.f - beta1)) : (m + (g - m) * (1.f - beta1));
-    u = SPARSE ? (u * beta2 + (g * g) * (1.f - beta2)) : (u + (g * g - u) * (1.f - beta2));
-    return theta - (m * lr_t) / (sqrtf(u) + eps);
-  }
-  return theta - lr_t * g;  // SGD without momentum
 }
 
 struct GainsParams {
@@ -635,6 +673,7 @@ struct GainsParams {
   int eval;             // 1: stand-alone gradient evaluation (no step in flight)
 };
 
+// Two adjacent channels per thread: z / y rows are read as float4 (two complex values), gain rows as float2.
 __global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
   const FitState* st = p.st;
   int src;
@@ -645,34 +684,40 @@ __global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
     src = (st->step - 1) & 1;
   }
   const int ant = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= p.nfp) return;
+  const int f = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (f >= p.nfp) return;  // nfp is a multiple of 16
   const float* __restrict__ gr = p.g_r[src];
   const float* __restrict__ gi = p.g_i[src];
   const size_t o = (size_t)ant * p.nfp + f;
-  float acc_r = 0.f, acc_i = 0.f;
+  float2 acc_r = make_float2(0.f, 0.f), acc_i = make_float2(0.f, 0.f);
   if (p.mode != 2) {
     const float alpha = st->alpha, beta = st->beta;
     const int e0 = p.ant_ptr[ant], e1 = p.ant_ptr[ant + 1];
-    auto accumulate = [&](int ent, float2 z, float2 y, float pr, float pi) {
+    auto one = [&](bool side1, float zx, float zy, float yx, float yy, float pr, float pi, float& ar, float& ai) {
       if (p.sum) {
-        z.x += alpha * y.x + beta * y.y;
-        z.y += alpha * y.y - beta * y.x;
+        zx += alpha * yx + beta * yy;
+        zy += alpha * yy - beta * yx;
       }
-      if ((ent & 1) == 0) {  // this antenna is ant0: conj(z) * g_partner
-        acc_r += z.x * pr + z.y * pi;
-        acc_i += z.x * pi - z.y * pr;
-      } else {               // this antenna is ant1: z * g_partner
-        acc_r += z.x * pr - z.y * pi;
-        acc_i += z.x * pi + z.y * pr;
+      if (!side1) {  // this antenna is ant0: conj(z) * g_partner
+        ar += zx * pr + zy * pi;
+        ai += zx * pi - zy * pr;
+      } else {       // this antenna is ant1: z * g_partner
+        ar += zx * pr - zy * pi;
+        ai += zx * pi + zy * pr;
       }
     };
+    auto accumulate = [&](int ent, const float4& z, const float4& y, const float2& pr, const float2& pi) {
+      const bool side1 = (ent & 1) != 0;
+      one(side1, z.x, z.y, y.x, y.y, pr.x, pi.x, acc_r.x, acc_i.x);
+      one(side1, z.z, z.w, y.z, y.w, pr.y, pi.y, acc_r.y, acc_i.y);
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr int U = 8;  // independent loads in flight per thread; the summation order stays e0..e1-1
     int e = e0;
     for (; e + U <= e1; e += U) {
       int ent[U], par[U];
-      float2 zz[U], yy[U];
-      float pr[U], pi[U];
+      float4 zz[U], yy[U];
+      float2 pr[U], pi[U];
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         ent[k] = p.ant_ent[e + k];
@@ -682,10 +727,10 @@ __global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
       for (int k = 0; k < U; ++k) {
         const size_t ob = (size_t)(ent[k] >> 1) * p.nfp + f;
         const size_t op = (size_t)par[k] * p.nfp + f;
-        zz[k] = p.z[ob];
-        yy[k] = p.sum ? p.y[ob] : make_float2(0.f, 0.f);
-        pr[k] = gr[op];
-        pi[k] = gi[op];
+        zz[k] = *reinterpret_cast<const float4*>(p.z + ob);
+        yy[k] = p.sum ? *reinterpret_cast<const float4*>(p.y + ob) : zero4;
+        pr[k] = *reinterpret_cast<const float2*>(gr + op);
+        pi[k] = *reinterpret_cast<const float2*>(gi + op);
       }
 #pragma unroll
       for (int k = 0; k < U; ++k) accumulate(ent[k], zz[k], yy[k], pr[k], pi[k]);
@@ -694,29 +739,116 @@ __global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
       const int ent = p.ant_ent[e];
       const size_t ob = (size_t)(ent >> 1) * p.nfp + f;
       const size_t op = (size_t)p.ant_partner[e] * p.nfp + f;
-      accumulate(ent, p.z[ob], p.sum ? p.y[ob] : make_float2(0.f, 0.f), gr[op], gi[op]);
+      accumulate(ent, *reinterpret_cast<const float4*>(p.z + ob), p.sum ? *reinterpret_cast<const float4*>(p.y + ob) : zero4,
+                 *reinterpret_cast<const float2*>(gr + op), *reinterpret_cast<const float2*>(gi + op));
     }
     if (p.grad_r) {
-      p.grad_r[o] = acc_r;
-      p.grad_i[o] = acc_i;
+      *reinterpret_cast<float2*>(p.grad_r + o) = acc_r;
+      *reinterpret_cast<float2*>(p.grad_i + o) = acc_i;
     }
     if (p.mode == 1) return;
   } else {
-    acc_r = p.grad_r[o];
-    acc_i = p.grad_i[o];
+    acc_r = *reinterpret_cast<const float2*>(p.grad_r + o);
+    acc_i = *reinterpret_cast<const float2*>(p.grad_i + o);
   }
-  float mr = p.m_r[o], ur = p.u_r[o], mi = p.m_i[o], ui = p.u_i[o];
-  const float nr = opt_step<true>(p.k.optimizer, gr[o], acc_r, mr, ur, st->lr_t, p.k.beta1, p.k.beta2, p.k.eps);
-  const float ni = opt_step<true>(p.k.optimizer, gi[o], acc_i, mi, ui, st->lr_t, p.k.beta1, p.k.beta2, p.k.eps);
-  p.m_r[o] = mr;
-  p.u_r[o] = ur;
-  p.m_i[o] = mi;
-  p.u_i[o] = ui;
-  p.g_r[src ^ 1][o] = nr;
-  p.g_i[src ^ 1][o] = ni;
-  if (st->snap && p.snap_r) {
-    p.snap_r[o] = nr;
-    p.snap_i[o] = ni;
+  const float lr_t = st->lr_t;
+  const float a_r[2] = {acc_r.x, acc_r.y}, a_i[2] = {acc_i.x, acc_i.y};
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const size_t oc = o + c;
+    float mr = p.m_r[oc], ur = p.u_r[oc], mi = p.m_i[oc], ui = p.u_i[oc];
+    const float nr = opt_step<true>(p.k.optimizer, gr[oc], a_r[c], mr, ur, lr_t, p.k.beta1, p.k.beta2, p.k.eps);
+    const float ni = opt_step<true>(p.k.optimizer, gi[oc], a_i[c], mi, ui, lr_t, p.k.beta1, p.k.beta2, p.k.eps);
+    p.m_r[oc] = mr;
+    p.u_r[oc] = ur;
+    p.m_i[oc] = mi;
+    p.u_i[oc] = ui;
+    p.g_r[src ^ 1][oc] = nr;
+    p.g_i[src ^ 1][oc] = ni;
+    if (st->snap && p.snap_r) {
+      p.snap_r[oc] = nr;
+      p.snap_i[oc] = ni;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// freeze_model (calibration.py:598-603): the foreground model never changes, so an iteration only needs the
+// elementwise part -- gains, model, residual, chi^2 and z -- over the N_D visibilities; the basis is not touched.
+// Grid-stride over (baseline, channel pairs); per-CTA partial sums in a fixed order.
+// ------------------------------------------------------------------------------------------------
+struct LightParams {
+  const float2* vout;   // [nslots][nfp] model visibilities, computed once per fit
+  const int* bl_slot;
+  const int* bl_ant0;
+  const int* bl_ant1;
+  const float* d_r;
+  const float* d_i;
+  const float* w;
+  const float* g_r[2];
+  const float* g_i[2];
+  float2* z;
+  float2* y;
+  double* partials;     // [gridDim.x][4]
+  const FitState* st;
+  int nfp;
+  long long nelem;      // nbls * nfp
+  int sum;
+};
+
+__global__ void __launch_bounds__(256) light_kernel(const LightParams p) {
+  __shared__ float red[8][4];
+  const FitState* st = p.st;
+  if (st->step > st->stop_after) return;
+  const int gsel = st->step & 1;
+  const float* __restrict__ g_r = p.g_r[gsel];
+  const float* __restrict__ g_i = p.g_i[gsel];
+  float loss_acc = 0.f, sr_acc = 0.f, si_acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < p.nelem; e += stride) {
+    const int b = (int)(e / p.nfp), f = (int)(e % p.nfp);
+    const float2 v = p.vout[(size_t)p.bl_slot[b] * p.nfp + f];
+    const float dr = p.d_r[e], di = p.d_i[e], w = p.w[e];
+    const size_t o0 = (size_t)p.bl_ant0[b] * p.nfp + f, o1 = (size_t)p.bl_ant1[b] * p.nfp + f;
+    const float gr0 = g_r[o0], gi0 = g_i[o0], gr1 = g_r[o1], gi1 = g_i[o1];
+    const float P = gr0 * gr1 + gi0 * gi1;
+    const float Q = gr0 * gi1 - gi0 * gr1;
+    const float mr = P * v.x + Q * v.y;
+    const float mi = P * v.y - Q * v.x;
+    const float rr = dr - mr, ri = di - mi;
+    loss_acc += (rr * rr + ri * ri) * w;
+    const float er = -2.f * w * rr, ei = -2.f * w * ri;
+    p.z[e] = make_float2(er * v.x + ei * v.y, er * v.y - ei * v.x);
+    if (p.sum) {
+      p.y[e] = make_float2(w * v.x, w * v.y);
+      sr_acc += w * mr;
+      si_acc += w * mi;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+    sr_acc += __shfl_xor_sync(0xffffffffu, sr_acc, off);
+    si_acc += __shfl_xor_sync(0xffffffffu, si_acc, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp][0] = loss_acc;
+    red[warp][1] = sr_acc;
+    red[warp][2] = si_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a += (double)red[w][0];
+      b += (double)red[w][1];
+      c += (double)red[w][2];
+    }
+    double* dst = p.partials + (size_t)blockIdx.x * 4;
+    dst[0] = a;
+    dst[1] = b;
+    dst[2] = c;
   }
 }
 

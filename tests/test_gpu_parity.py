@@ -124,6 +124,19 @@ def test_freeze_model_and_graph(native_built):
         assert np.array_equal(c_r, prob.c0_r) and np.array_equal(c_i, prob.c0_i)
 
 
+def test_fused_tail_update_is_bit_identical_to_split_step(native_built):
+    """The optional in-kernel coefficient update (north_star item 4) must give exactly the split step's results."""
+    prob = small_problem("hera37", init_gain_scatter=0.02, coeff_error=0.05)
+    outs = []
+    for fuse in (False, True):
+        plan = _plan(prob)
+        hist, res = plan.fit(optimizer="Adam", maxsteps=25, tol=0.0, learning_rate=1e-2, fuse_tail_update=fuse)
+        outs.append((hist,) + plan.get_coeffs() + plan.get_gains())
+        plan.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_model_and_determinism(native_built):
     prob = small_problem("hera37", init_gain_scatter=0.02, coeff_error=0.05)
     t = reference_tensors(prob, np.float64)
