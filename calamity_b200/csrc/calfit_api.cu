@@ -56,7 +56,7 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
-static constexpr int RPT = 11;
+static constexpr int RPT_DEFAULT = 11;  // steps per warp: 11 -> 2 CTAs/SM; 7 -> 3 CTAs/SM (smaller tiles)
 static constexpr int NWARP = 8;
 static constexpr int SMAX = 8;
 
@@ -100,7 +100,7 @@ using namespace calb2;
 
 struct calb2_plan {
   int device = 0, nants = 0, nf = 0, ngroups = 0;
-  int FL = 0, G = 0, FT = 0, KMAX = 0, nfp = 0, ntiles = 0;
+  int FL = 0, G = 0, FT = 0, KMAX = 0, nfp = 0, ntiles = 0, RPT = RPT_DEFAULT;
   long long nbls = 0, nslots = 0, ncoef = 0, rows_total = 0, a_floats = 0, n_a_nz = 0;
   // host copies of the description
   std::vector<int> grp_ncomp, grp_nslots, grp_slot0, grp_coef0, slot_nbls, slot_grp, slot_row0, slot_bl0, slot_item,
@@ -152,50 +152,87 @@ static int dalloc(DevBuf<T>& buf, size_t n, calb2_plan* pl, bool zero = true) {
   return 0;
 }
 
-static int choose_fl(const calb2_plan_desc* d, int* fl_out) {
+// Rows the greedy in-order packing would leave unused, as a fraction of the staged tile capacity.
+static double packing_fill(const calb2_plan_desc* d, int fl, int RPT) {
+  const int G = 32 / fl, kmax = NWARP * RPT * G;
+  long long rows = 0, items = 0;
+  int cur_rows = 0, cur_slots = 0;
+  for (int g = 0; g < d->ngroups; ++g) {
+    const int rp = std::max(G, ((d->group_ncomp[g] + G - 1) / G) * G);
+    for (int s = 0; s < d->group_nslots[g]; ++s) {
+      if (cur_slots > 0 && (cur_rows + rp > kmax || cur_slots >= SMAX)) {
+        ++items;
+        cur_rows = cur_slots = 0;
+      }
+      cur_rows += rp;
+      cur_slots += 1;
+      rows += rp;
+    }
+  }
+  if (cur_slots) ++items;
+  return items ? (double)rows / ((double)items * kmax) : 0.0;
+}
+
+// Tile width: 64- and 32-channel tiles stream equally well, 16 is measurably worse (64-byte row segments), so
+// 16 is only used when a group's basis does not fit otherwise; between 64 and 32 the better-filled packing wins
+// (HERA-128: 0.77 vs 0.89 fill -> +10 % throughput at 32; HERA-37: 0.86 vs 0.43 -> 64).
+static int choose_fl(const calb2_plan_desc* d, int RPT, int* fl_out) {
   int maxc = 0;
   for (int g = 0; g < d->ngroups; ++g) maxc = std::max(maxc, d->group_ncomp[g]);
-  const int cands[3] = {16, 8, 4};
+  auto fits = [&](int fl) {
+    const int G = 32 / fl;
+    return ((maxc + G - 1) / G) * G <= NWARP * RPT * G;
+  };
   if (d->tile_freqs) {
     const int fl = d->tile_freqs / 4;
     if (d->tile_freqs % 4 || (fl != 16 && fl != 8 && fl != 4)) return fail(CALB2_ERR_ARG, "tile_freqs must be 16, 32 or 64");
-    const int G = 32 / fl;
-    if (((maxc + G - 1) / G) * G > NWARP * RPT * G)
+    if (!fits(fl))
       return fail(CALB2_ERR_UNSUPPORTED, "a group has %d basis vectors; tile_freqs=%d stages at most %d", maxc,
-                  d->tile_freqs, NWARP * RPT * G);
+                  d->tile_freqs, NWARP * RPT * (32 / fl));
     *fl_out = fl;
     return 0;
   }
-  for (int fl : cands) {
-    const int G = 32 / fl;
-    if (((maxc + G - 1) / G) * G <= NWARP * RPT * G) {
-      *fl_out = fl;
-      return 0;
-    }
+  if (fits(16)) {
+    *fl_out = packing_fill(d, 8, RPT) > packing_fill(d, 16, RPT) + 0.02 ? 8 : 16;
+    return 0;
+  }
+  if (fits(8)) {
+    *fl_out = 8;
+    return 0;
+  }
+  if (fits(4)) {
+    *fl_out = 4;
+    return 0;
   }
   return fail(CALB2_ERR_UNSUPPORTED, "a group has %d basis vectors; at most %d are supported", maxc, NWARP * RPT * 8);
 }
 
-template <int FL, bool SUM>
+template <int FL, bool SUM, int RPT, int MINB>
 static cudaError_t launch_heavy_t(const HeavyParams& hp, int nitems, cudaStream_t s) {
   using C = HeavyCfg<FL, SUM, RPT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(heavy_kernel<FL, SUM, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(heavy_kernel<FL, SUM, RPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  heavy_kernel<FL, SUM, RPT><<<nitems, C::NTHR, C::SMEM_BYTES, s>>>(hp);
+  heavy_kernel<FL, SUM, RPT, MINB><<<nitems, C::NTHR, C::SMEM_BYTES, s>>>(hp);
   return cudaGetLastError();
 }
 
-static cudaError_t launch_heavy(int FL, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
+template <int RPT, int MINB>
+static cudaError_t launch_heavy_r(int FL, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
   switch (FL) {
-    case 16: return sum ? launch_heavy_t<16, true>(hp, nitems, s) : launch_heavy_t<16, false>(hp, nitems, s);
-    case 8: return sum ? launch_heavy_t<8, true>(hp, nitems, s) : launch_heavy_t<8, false>(hp, nitems, s);
-    default: return sum ? launch_heavy_t<4, true>(hp, nitems, s) : launch_heavy_t<4, false>(hp, nitems, s);
+    case 16: return sum ? launch_heavy_t<16, true, RPT, MINB>(hp, nitems, s) : launch_heavy_t<16, false, RPT, MINB>(hp, nitems, s);
+    case 8: return sum ? launch_heavy_t<8, true, RPT, MINB>(hp, nitems, s) : launch_heavy_t<8, false, RPT, MINB>(hp, nitems, s);
+    default: return sum ? launch_heavy_t<4, true, RPT, MINB>(hp, nitems, s) : launch_heavy_t<4, false, RPT, MINB>(hp, nitems, s);
   }
+}
+
+static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
+  if (pl->RPT == 7) return launch_heavy_r<7, 3>(pl->FL, sum, hp, nitems, s);
+  return launch_heavy_r<11, 2>(pl->FL, sum, hp, nitems, s);
 }
 
 static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, int store_v, int init_mode) {
@@ -402,7 +439,7 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     HeavyParams hp = heavy_params(pl, pl->state.p, sum, 0, 0);
     hp.fuse_update = fuse ? 1 : 0;
     hp.k = k;
-    CU(launch_heavy(pl->FL, sum, hp, (int)pl->items.size(), pl->stream));
+    CU(launch_heavy(pl, sum, hp, (int)pl->items.size(), pl->stream));
   }
   if (ev1) CU(cudaEventRecord(ev1, pl->stream));
   FinalizeParams fp{};
@@ -463,7 +500,7 @@ static int init_coeffs_impl(calb2_plan* pl, const float* sky_r, const float* sky
   HeavyParams hp = heavy_params(pl, pl->state_eval.p, false, 0, 1);
   hp.d_r = pl->sky_r.p;
   hp.d_i = pl->sky_i.p;
-  CU(launch_heavy(pl->FL, false, hp, (int)pl->items.size(), pl->stream));
+  CU(launch_heavy(pl, false, hp, (int)pl->items.size(), pl->stream));
   FitConsts k{};
   coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(coeff_params(pl, pl->state_eval.p, k, 1, false));
   CU(cudaGetLastError());
@@ -536,8 +573,10 @@ const char* calb2_version(void) { return "calamity_b200 0.1 (sm_100a)"; }
 int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   if (!d || !out) return fail(CALB2_ERR_ARG, "null argument");
   if (d->nants <= 0 || d->nfreqs <= 0 || d->ngroups <= 0) return fail(CALB2_ERR_ARG, "empty problem");
+  int rpt = RPT_DEFAULT;
+  if (const char* e = getenv("CALB2_RPT")) rpt = atoi(e) == 7 ? 7 : 11;
   int fl = 0;
-  if (int r = choose_fl(d, &fl)) return r;
+  if (int r = choose_fl(d, rpt, &fl)) return r;
   CU(cudaSetDevice(d->device));
   calb2_plan* pl = new calb2_plan();
   pl->device = d->device;
@@ -547,7 +586,8 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   pl->FL = fl;
   pl->G = 32 / fl;
   pl->FT = 4 * fl;
-  pl->KMAX = NWARP * RPT * pl->G;
+  pl->RPT = rpt;
+  pl->KMAX = NWARP * rpt * pl->G;
   pl->ntiles = (pl->nf + pl->FT - 1) / pl->FT;
   pl->nfp = pl->ntiles * pl->FT;
   const int G = pl->G;
@@ -905,7 +945,7 @@ static int run_forward_store_v(calb2_plan* pl) {
   if (int r = ensure_vout(pl)) return r;
   if (int r = set_eval_state(pl)) return r;
   HeavyParams hp = heavy_params(pl, pl->state_eval.p, false, 1, 0);
-  CU(launch_heavy(pl->FL, false, hp, (int)pl->items.size(), pl->stream));
+  CU(launch_heavy(pl, false, hp, (int)pl->items.size(), pl->stream));
   return 0;
 }
 
@@ -998,7 +1038,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, 
   k.prior_r = prior_r;
   k.prior_i = prior_i;
   HeavyParams hp = heavy_params(pl, pl->state_eval.p, sum, 0, 0);
-  CU(launch_heavy(pl->FL, sum, hp, (int)pl->items.size(), pl->stream));
+  CU(launch_heavy(pl, sum, hp, (int)pl->items.size(), pl->stream));
   FinalizeParams fp{};
   fp.partials = pl->partials.p;
   fp.nitems = (int)pl->items.size();

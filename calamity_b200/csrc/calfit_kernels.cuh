@@ -204,8 +204,8 @@ struct HeavyCfg {
   static constexpr int SMEM_BYTES = OFF_MBAR + NBUF * 8;
 };
 
-template <int FL, bool SUM, int RPT>
-__global__ void __launch_bounds__(256, 2) heavy_kernel(const HeavyParams p) {
+template <int FL, bool SUM, int RPT, int MINB>
+__global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
   using C = HeavyCfg<FL, SUM, RPT>;
   constexpr int G = C::G, FT = C::FT, NQ = C::NQ;
   extern __shared__ __align__(128) unsigned char smem[];
