@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libcalamity_b200.so")
+_LIB_PATH = os.environ.get("CALB2_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libcalamity_b200.so")
 _lib = None
 
 

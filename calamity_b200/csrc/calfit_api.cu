@@ -70,6 +70,8 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ IdBlob, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -88,6 +90,8 @@ static int load_nccl(const char* path) {
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.handle, "ncclAllReduce");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.handle, "ncclCommDestroy");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.handle, "ncclGetErrorString");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(g_nccl.handle, "ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(g_nccl.handle, "ncclGroupEnd");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
     return fail(CALB2_ERR_NCCL, "NCCL symbols missing");
   return 0;
@@ -447,29 +451,44 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
   fp.k = k;
   fp.hist = hist;
   fp.eval_only = 0;
+  dim3 ggrid((pl->nfp / 2 + 127) / 128, pl->nants);
+  const size_t ngrad = (size_t)2 * pl->nants * pl->nfp;
   if (pl->nranks > 1) {
     reduce_partials_kernel<<<1, 1024, 0, pl->stream>>>(partials, npartials, pl->comm_scalars.p);
     CU(cudaGetLastError());
-    if (int r = all_reduce(pl, pl->comm_scalars.p, 4, NCCL_FLOAT64)) return r;
+    *launches += 1;
     fp.partials = pl->comm_scalars.p;
     fp.nitems = 1;
-    *launches += 1;
-  } else {
-    fp.partials = partials;
-    fp.nitems = npartials;
-  }
-  finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
-  CU(cudaGetLastError());
-  dim3 ggrid((pl->nfp / 2 + 127) / 128, pl->nants);
-  if (pl->nranks > 1) {
-    gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 1, sum, 0));
-    CU(cudaGetLastError());
-    // real and imaginary gradient tables are adjacent halves of one allocation
-    if (int r = all_reduce(pl, pl->ggrad_r.p, (size_t)2 * pl->nants * pl->nfp, NCCL_FLOAT32)) return r;
+    if (!sum && g_nccl.GroupStart && g_nccl.GroupEnd) {
+      // without the regulariser the gain-gradient reduce does not need finalize's alpha/beta: reduce first and
+      // send scalars + gradient tables in ONE grouped NCCL launch
+      gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 4, sum, 0));
+      CU(cudaGetLastError());
+      g_nccl.GroupStart();
+      int r1 = all_reduce(pl, pl->comm_scalars.p, 4, NCCL_FLOAT64);
+      int r2 = all_reduce(pl, pl->ggrad_r.p, ngrad, NCCL_FLOAT32);
+      g_nccl.GroupEnd();
+      if (r1) return r1;
+      if (r2) return r2;
+      finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
+      CU(cudaGetLastError());
+    } else {
+      if (int r = all_reduce(pl, pl->comm_scalars.p, 4, NCCL_FLOAT64)) return r;
+      finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
+      CU(cudaGetLastError());
+      gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 1, sum, 0));
+      CU(cudaGetLastError());
+      // real and imaginary gradient tables are adjacent halves of one allocation
+      if (int r = all_reduce(pl, pl->ggrad_r.p, ngrad, NCCL_FLOAT32)) return r;
+    }
     gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 2, sum, 0));
     CU(cudaGetLastError());
     *launches += 1;
   } else {
+    fp.partials = partials;
+    fp.nitems = npartials;
+    finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
+    CU(cudaGetLastError());
     gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 0, sum, 0));
     CU(cudaGetLastError());
   }
@@ -671,6 +690,24 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     pl->n_a_nz += (long long)ncomp * pl->nf;
   }
   close_item();
+  // Launch order = longest first (rows, then slots): the grid is consumed in index order, so the kernel's tail
+  // is made of the cheapest items.  Only the ORDER of the descriptors changes; rows / slots keep their places.
+  if (!getenv("CALB2_NO_LPT")) {
+    std::vector<int> order(pl->items.size());
+    for (size_t n = 0; n < order.size(); ++n) order[n] = (int)n;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (pl->items[a].nrows != pl->items[b].nrows) return pl->items[a].nrows > pl->items[b].nrows;
+      return pl->items[a].nslots > pl->items[b].nslots;
+    });
+    std::vector<ItemDesc> sorted(pl->items.size());
+    std::vector<int> new_index(pl->items.size());
+    for (size_t n = 0; n < order.size(); ++n) {
+      sorted[n] = pl->items[order[n]];
+      new_index[order[n]] = (int)n;
+    }
+    pl->items.swap(sorted);
+    for (long long s = 0; s < ns; ++s) pl->slot_item[s] = new_index[pl->slot_item[s]];
+  }
   pl->slot_row0[ns] = (int)rows;
   pl->rows_total = rows;
   pl->a_floats = rows * (long long)pl->nfp;

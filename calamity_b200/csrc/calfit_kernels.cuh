@@ -106,6 +106,9 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -237,8 +240,12 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     mbar_fence_init();
-    mbar_expect_tx(&mbar[0], tile_bytes);  // tile 0 streams in while the item's metadata is gathered
+    mbar_expect_tx(&mbar[0], tile_bytes);  // tiles 0 and 1 stream in while the item's metadata is gathered
     bulk_g2s(Abuf, Abase, tile_bytes, &mbar[0]);
+    if (p.ntiles > 1) {
+      mbar_expect_tx(&mbar[1], tile_bytes);
+      bulk_g2s(Abuf + C::TILE_FLOATS, Abase + (size_t)it.nrows * FT, tile_bytes, &mbar[1]);
+    }
   }
   // Rows past the item's last row are zero in both tile buffers (the bulk copies never touch them) and
   // carry zero coefficients, so every warp that owns at least one row runs all RPT steps unguarded.
@@ -331,10 +338,6 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
 
   for (int j = 0; j < p.ntiles; ++j) {
     const int buf = j & 1;
-    if (tid == 0 && j + 1 < p.ntiles) {
-      mbar_expect_tx(&mbar[buf ^ 1], tile_bytes);
-      bulk_g2s(Abuf + (buf ^ 1) * C::TILE_FLOATS, Abase + (size_t)(j + 1) * it.nrows * FT, tile_bytes, &mbar[buf ^ 1]);
-    }
     mbar_wait(&mbar[buf], (j >> 1) & 1);
     const float* Ab = Abuf + buf * C::TILE_FLOATS + row_off;
     const float2* cb = cbuf + step_base * G + usub;
@@ -397,9 +400,12 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
         const int fg = j * FT + f;
         const int w_lo = slot_step0[s] / RPT, w_hi = (slot_step0[s + 1] - 1) / RPT;
         float v_r = 0.f, v_i = 0.f;
-        for (int w = w_lo; w <= w_hi; ++w) {
-          v_r += vpart[((w + s) * 2 + 0) * FT + f];
-          v_i += vpart[((w + s) * 2 + 1) * FT + f];
+#pragma unroll
+        for (int w = 0; w < C::NWARP; ++w) {  // all loads issue back to back; summation order is fixed
+          if (w >= w_lo && w <= w_hi) {
+            v_r += vpart[((w + s) * 2 + 0) * FT + f];
+            v_i += vpart[((w + s) * 2 + 1) * FT + f];
+          }
         }
         float qr = 0.f, qi = 0.f, pw = 0.f, qw = 0.f;
         const int b_first = slot_bl0[s], b_end = slot_bl0[s + 1];
@@ -488,8 +494,15 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
         }
       }
     }
-    __syncthreads();  // tile buffer, vpart and qbuf are free for the next tile
+    // All warps are done with the tile buffer: refill it with tile j + 2.  (Replacing this barrier by an mbarrier
+    // "buffer empty" handshake that only thread 0 waits on was measured 23 % SLOWER: 151 vs 196 it/s at HERA-350.)
+    __syncthreads();
+    if (tid == 0 && j + 2 < p.ntiles) {
+      mbar_expect_tx(&mbar[buf], tile_bytes);
+      bulk_g2s(Abuf + buf * C::TILE_FLOATS, Abase + (size_t)(j + 2) * it.nrows * FT, tile_bytes, &mbar[buf]);
+    }
   }
+  __syncthreads();  // the epilogue reuses the tile buffers
 
   // ---------------- item epilogue: lane reduction of the backward sums ----------------
   // The reduced sums are staged in shared memory (the tile buffers are free now) so that the write-out --
@@ -668,7 +681,7 @@ struct GainsParams {
   FitConsts k;
   int nfp;
   int nants;
-  int mode;             // 0: reduce + update; 1: reduce only -> grad; 2: update only from grad
+  int mode;             // 0: reduce + update; 1: reduce only -> grad; 2: update only from grad; 4: as 1, before finalize
   int sum;
   int eval;             // 1: stand-alone gradient evaluation (no step in flight)
 };
@@ -679,6 +692,9 @@ __global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
   int src;
   if (p.eval) {
     src = st->step & 1;  // stand-alone gradient evaluation at the current parameters
+  } else if (p.mode == 4) {
+    if (st->step > st->stop_after) return;  // reduce-only pass that runs BEFORE finalize_kernel of this step
+    src = st->step & 1;
   } else {
     if (!st->upd_active) return;
     src = (st->step - 1) & 1;
@@ -746,7 +762,7 @@ __global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
       *reinterpret_cast<float2*>(p.grad_r + o) = acc_r;
       *reinterpret_cast<float2*>(p.grad_i + o) = acc_i;
     }
-    if (p.mode == 1) return;
+    if (p.mode == 1 || p.mode == 4) return;
   } else {
     acc_r = *reinterpret_cast<const float2*>(p.grad_r + o);
     acc_i = *reinterpret_cast<const float2*>(p.grad_i + o);

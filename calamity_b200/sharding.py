@@ -61,7 +61,15 @@ class Shard:
         return np.ascontiguousarray(flat[self.coef0 : self.coef1])
 
 
+def group_costs(layout):
+    """Per-group cost in 4-byte words per channel: basis rows (ncomp per slot) plus the per-baseline traffic of the
+    iteration -- data_r/data_i/weights read (3), z written (2) and read at both antennas (4), gains gathered (~1):
+    about 10 words per baseline.  Balancing on basis bytes alone overloads the rank that owns the short baselines."""
+    nbl_per_group = np.add.reduceat(layout.slot_nbls, np.concatenate([[0], np.cumsum(layout.group_nslots)[:-1]]))
+    return layout.group_ncomp.astype(np.int64) * layout.group_nslots + 10 * nbl_per_group.astype(np.int64)
+
+
 def make_shard(full_layout, rank, nranks):
-    ranges = partition_groups(full_layout.group_ncomp.astype(np.int64) * full_layout.group_nslots, nranks)
+    ranges = partition_groups(group_costs(full_layout), nranks)
     g0, g1 = ranges[rank]
     return Shard(full_layout, g0, g1)
