@@ -25,9 +25,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# the contract is ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# The contract is ONE JSON line on stdout.  Native libraries (NCCL prints "NCCL version ..." when NCCL_DEBUG is
+# VERSION or higher) write to file descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the
+# result line goes out through a private duplicate of the original stdout.
+sys.stdout.flush()
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 METRIC = "fit_iterations_per_sec"
 UNIT = "it/s"
@@ -161,7 +170,7 @@ def run_reference_arm(args, rank, world):
                                  "installable in this image); never the reference's own TensorFlow build"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, prob, sizes, world):
@@ -338,7 +347,7 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     plan.close()
     if dist is not None:
         dist.barrier()
