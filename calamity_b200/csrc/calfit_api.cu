@@ -56,7 +56,7 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
-static constexpr int RPT_DEFAULT = 11;  // steps per warp: 11 -> 2 CTAs/SM; 7 -> 3 CTAs/SM (smaller tiles)
+static constexpr int RPT_DEFAULT = 11;  // steps per warp: 11 -> 45 KB tiles, 2 CTAs/SM (7 -> 3 CTAs/SM was measured slower)
 static constexpr int NWARP = 8;
 static constexpr int SMAX = 8;
 
@@ -128,7 +128,7 @@ struct calb2_plan {
   FitState* h_state = nullptr;  // pinned
   cudaStream_t stream = nullptr;
   int cur_buf = 0;
-  bool have_data = false, have_gains = false, have_coeffs = false, basis_complete = false, all_single_slot = true;
+  bool have_data = false, have_gains = false, have_coeffs = false, basis_complete = false, all_single_slot = true, all_single_bl = true;
   int light_blocks = 0;
   DevBuf<double> light_partials;
   long long basis_groups_set = 0;
@@ -211,32 +211,36 @@ static int choose_fl(const calb2_plan_desc* d, int RPT, int* fl_out) {
   return fail(CALB2_ERR_UNSUPPORTED, "a group has %d basis vectors; at most %d are supported", maxc, NWARP * RPT * 8);
 }
 
-template <int FL, bool SUM, int RPT, int MINB>
+template <int FL, bool SUM, int QMODE>
 static cudaError_t launch_heavy_t(const HeavyParams& hp, int nitems, cudaStream_t s) {
+  constexpr int RPT = RPT_DEFAULT, MINB = 2;
   using C = HeavyCfg<FL, SUM, RPT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(heavy_kernel<FL, SUM, RPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(heavy_kernel<FL, SUM, RPT, MINB, QMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  heavy_kernel<FL, SUM, RPT, MINB><<<nitems, C::NTHR, C::SMEM_BYTES, s>>>(hp);
+  heavy_kernel<FL, SUM, RPT, MINB, QMODE><<<nitems, C::NTHR, C::SMEM_BYTES, s>>>(hp);
   return cudaGetLastError();
 }
 
-template <int RPT, int MINB>
-static cudaError_t launch_heavy_r(int FL, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
-  switch (FL) {
-    case 16: return sum ? launch_heavy_t<16, true, RPT, MINB>(hp, nitems, s) : launch_heavy_t<16, false, RPT, MINB>(hp, nitems, s);
-    case 8: return sum ? launch_heavy_t<8, true, RPT, MINB>(hp, nitems, s) : launch_heavy_t<8, false, RPT, MINB>(hp, nitems, s);
-    default: return sum ? launch_heavy_t<4, true, RPT, MINB>(hp, nitems, s) : launch_heavy_t<4, false, RPT, MINB>(hp, nitems, s);
-  }
+template <int FL>
+static cudaError_t launch_heavy_f(bool sum, int qmode, const HeavyParams& hp, int nitems, cudaStream_t s) {
+  if (qmode == QM_INIT) return launch_heavy_t<FL, false, QM_INIT>(hp, nitems, s);
+  if (qmode == QM_SINGLE)
+    return sum ? launch_heavy_t<FL, true, QM_SINGLE>(hp, nitems, s) : launch_heavy_t<FL, false, QM_SINGLE>(hp, nitems, s);
+  return sum ? launch_heavy_t<FL, true, QM_GENERAL>(hp, nitems, s) : launch_heavy_t<FL, false, QM_GENERAL>(hp, nitems, s);
 }
 
 static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
-  if (pl->RPT == 7) return launch_heavy_r<7, 3>(pl->FL, sum, hp, nitems, s);
-  return launch_heavy_r<11, 2>(pl->FL, sum, hp, nitems, s);
+  const int qmode = hp.init_mode ? QM_INIT : (pl->all_single_bl ? QM_SINGLE : QM_GENERAL);
+  switch (pl->FL) {
+    case 16: return launch_heavy_f<16>(sum, qmode, hp, nitems, s);
+    case 8: return launch_heavy_f<8>(sum, qmode, hp, nitems, s);
+    default: return launch_heavy_f<4>(sum, qmode, hp, nitems, s);
+  }
 }
 
 static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, int store_v, int init_mode) {
@@ -592,8 +596,7 @@ const char* calb2_version(void) { return "calamity_b200 0.1 (sm_100a)"; }
 int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   if (!d || !out) return fail(CALB2_ERR_ARG, "null argument");
   if (d->nants <= 0 || d->nfreqs <= 0 || d->ngroups <= 0) return fail(CALB2_ERR_ARG, "empty problem");
-  int rpt = RPT_DEFAULT;
-  if (const char* e = getenv("CALB2_RPT")) rpt = atoi(e) == 7 ? 7 : 11;
+  const int rpt = RPT_DEFAULT;
   int fl = 0;
   if (int r = choose_fl(d, rpt, &fl)) return r;
   CU(cudaSetDevice(d->device));
@@ -638,6 +641,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     for (int s = 0; s < d->group_nslots[g]; ++s) pl->slot_grp[pl->grp_slot0[g] + s] = g;
   for (long long s = 0; s < ns; ++s) {
     pl->slot_bl0[s] = (int)nb;
+    if (pl->slot_nbls[s] != 1) pl->all_single_bl = false;
     nb += pl->slot_nbls[s];
   }
   pl->slot_bl0[ns] = (int)nb;

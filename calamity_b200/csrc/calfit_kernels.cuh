@@ -207,7 +207,14 @@ struct HeavyCfg {
   static constexpr int SMEM_BYTES = OFF_MBAR + NBUF * 8;
 };
 
-template <int FL, bool SUM, int RPT, int MINB>
+// QMODE specialises phase Q, which is a serial per-warp instruction stream on the critical path of every tile
+// (measured with clock64: ~1500 of ~3800 cycles per tile before the specialisation):
+//   QM_SINGLE   every slot has exactly one baseline (the per-baseline DPSS layout): straight-line code
+//   QM_GENERAL  slots with several (redundant) baselines: the first from prefetched registers, the rest in a loop
+//   QM_INIT     dL/dv := data * (w != 0), the right-hand side of the coefficient initialisation
+enum { QM_SINGLE = 0, QM_GENERAL = 1, QM_INIT = 2 };
+
+template <int FL, bool SUM, int RPT, int MINB, int QMODE>
 __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
   using C = HeavyCfg<FL, SUM, RPT>;
   constexpr int G = C::G, FT = C::FT, NQ = C::NQ;
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
   }
   for (int r = tid; r < C::KMAX; r += C::NTHR) {
     float2 c = make_float2(0.f, 0.f);
-    if (r < it.nrows && !p.init_mode) {
+    if (r < it.nrows && QMODE != QM_INIT) {
       const int ci = p.row_coef[it.row0 + r];
       if (ci >= 0) c = make_float2(p.c_r[ci], p.c_i[ci]);
     }
@@ -290,21 +297,34 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
     }
   }
 
-  // Q-phase inputs of the first baseline of each (slot, channel) element this thread owns are prefetched
-  // into registers one tile ahead: issued right after Q(j) for tile j + 1, so their DRAM/L2 latency is
-  // covered by phase B, the tile wait and phase F instead of being exposed in every tile.
+  // Phase Q: this thread owns the (slot, channel) elements e = tid + m * NTHR of EVERY tile, so everything that does
+  // not depend on the tile index is worked out once per item: offsets of the first baseline's data / gain rows, the
+  // warps whose partial sums belong to the slot (bit mask), the partial-sum and q-buffer addresses.  The inputs of
+  // the first baseline are prefetched into registers one tile ahead (issued right after Q(j) for tile j + 1), so
+  // their DRAM / L2 latency is covered by phase B, the tile wait and phase F.
   constexpr int EPT = (C::SMAX * FT + C::NTHR - 1) / C::NTHR;
   float pf[EPT][7];
-  int qoff[EPT], qoff0[EPT], qoff1[EPT];  // element offsets at tile 0 (data row, ant0 row, ant1 row)
+  int qoff[EPT], qoff0[EPT], qoff1[EPT];  // element offsets at tile 0 (data row, ant0 row, ant1 row); qoff < 0: none
+  int q_vp[EPT], q_qb[EPT], q_b0[EPT], q_nb[EPT], q_vo[EPT];
+  unsigned q_wmask[EPT];
 #pragma unroll
   for (int m = 0; m < EPT; ++m) {
     const int e = tid + m * C::NTHR;
     qoff[m] = -1;
     qoff0[m] = qoff1[m] = 0;
+    q_vp[m] = q_qb[m] = q_b0[m] = q_nb[m] = q_vo[m] = 0;
+    q_wmask[m] = 0u;
     if (e < it.nslots * FT) {
       const int s = e / FT, f = e % FT;
       const int b = slot_bl0[s];
-      if (b < slot_bl0[s + 1]) {
+      const int w_lo = slot_step0[s] / RPT, w_hi = (slot_step0[s + 1] - 1) / RPT;
+      q_wmask[m] = ((2u << w_hi) - 1u) & ~((1u << w_lo) - 1u);
+      q_vp[m] = (s * 2) * FT + f;        // partial of warp w: + w * 2 * FT (real), + FT more (imaginary)
+      q_qb[m] = (s * NQ) * FT + f;
+      q_b0[m] = b;
+      q_nb[m] = slot_bl0[s + 1] - b;
+      q_vo[m] = (it.slot0 + s) * p.nfp + f;
+      if (q_nb[m] > 0) {
         qoff[m] = b * p.nfp + f;
         qoff0[m] = p.bl_ant0[b] * p.nfp + f;
         qoff1[m] = p.bl_ant1[b] * p.nfp + f;
@@ -315,14 +335,17 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
 #pragma unroll
     for (int m = 0; m < EPT; ++m) {
       if (qoff[m] >= 0) {
-        const int o = qoff[m] + jt * FT, o0 = qoff0[m] + jt * FT, o1 = qoff1[m] + jt * FT;
+        const int o = qoff[m] + jt * FT;
         pf[m][0] = p.d_r[o];
         pf[m][1] = p.d_i[o];
         pf[m][2] = p.w[o];
-        pf[m][3] = g_r[o0];
-        pf[m][4] = g_i[o0];
-        pf[m][5] = g_r[o1];
-        pf[m][6] = g_i[o1];
+        if (QMODE != QM_INIT) {
+          const int o0 = qoff0[m] + jt * FT, o1 = qoff1[m] + jt * FT;
+          pf[m][3] = g_r[o0];
+          pf[m][4] = g_i[o0];
+          pf[m][5] = g_r[o1];
+          pf[m][6] = g_i[o1];
+        }
       }
     }
   };
@@ -394,38 +417,18 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
     // ---------------- phase Q: gains, model, residual, chi^2, dL/dv ----------------
 #pragma unroll
     for (int m = 0; m < EPT; ++m) {
-      const int e = tid + m * C::NTHR;
-      if (e < it.nslots * FT) {
-        const int s = e / FT, f = e % FT;
-        const int fg = j * FT + f;
-        const int w_lo = slot_step0[s] / RPT, w_hi = (slot_step0[s + 1] - 1) / RPT;
+      if (q_wmask[m] != 0u) {  // this thread owns an element (uniform over tiles)
         float v_r = 0.f, v_i = 0.f;
 #pragma unroll
         for (int w = 0; w < C::NWARP; ++w) {  // all loads issue back to back; summation order is fixed
-          if (w >= w_lo && w <= w_hi) {
-            v_r += vpart[((w + s) * 2 + 0) * FT + f];
-            v_i += vpart[((w + s) * 2 + 1) * FT + f];
+          if ((q_wmask[m] >> w) & 1u) {
+            v_r += vpart[q_vp[m] + w * 2 * FT];
+            v_i += vpart[q_vp[m] + w * 2 * FT + FT];
           }
         }
         float qr = 0.f, qi = 0.f, pw = 0.f, qw = 0.f;
-        const int b_first = slot_bl0[s], b_end = slot_bl0[s + 1];
-        for (int b = b_first; b < b_end; ++b) {
-          const size_t o = (size_t)b * p.nfp + fg;
-          float dr, di, w, gr0, gi0, gr1, gi1;
-          if (b == b_first) {
-            dr = pf[m][0]; di = pf[m][1]; w = pf[m][2];
-            gr0 = pf[m][3]; gi0 = pf[m][4]; gr1 = pf[m][5]; gi1 = pf[m][6];
-          } else {
-            dr = p.d_r[o]; di = p.d_i[o]; w = p.w[o];
-            const size_t o0 = (size_t)p.bl_ant0[b] * p.nfp + fg, o1 = (size_t)p.bl_ant1[b] * p.nfp + fg;
-            gr0 = g_r[o0]; gi0 = g_i[o0]; gr1 = g_r[o1]; gi1 = g_i[o1];
-          }
-          if (p.init_mode) {  // right-hand side of the coefficient initialisation: data * (w != 0)
-            const float msk = (fabsf(w) <= 1e-8f) ? 0.f : 1.f;  // np.isclose(w, 0): |w| <= atol = 1e-8
-            qr += dr * msk;
-            qi += di * msk;
-            continue;
-          }
+        // one visibility: model = g_i conj(g_j) v, weighted residual, chi^2, z, dL/dv (calibration.py:1593-1609)
+        auto visibility = [&](int o, float dr, float di, float w, float gr0, float gi0, float gr1, float gi1) {
           const float P = gr0 * gr1 + gi0 * gi1;
           const float Q = gr0 * gi1 - gi0 * gr1;
           const float mr = P * v_r + Q * v_i;
@@ -443,14 +446,38 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
             pw += P * w;
             qw += Q * w;
           }
+        };
+        if (QMODE == QM_INIT) {  // right-hand side of the coefficient initialisation: data * (w != 0)
+          if (qoff[m] >= 0) {
+            const float msk0 = (fabsf(pf[m][2]) <= 1e-8f) ? 0.f : 1.f;  // np.isclose(w, 0): |w| <= atol = 1e-8
+            qr = pf[m][0] * msk0;
+            qi = pf[m][1] * msk0;
+            for (int n = 1; n < q_nb[m]; ++n) {
+              const size_t o = (size_t)(q_b0[m] + n) * p.nfp + (qoff[m] - q_b0[m] * p.nfp) + j * FT;
+              const float msk = (fabsf(p.w[o]) <= 1e-8f) ? 0.f : 1.f;
+              qr += p.d_r[o] * msk;
+              qi += p.d_i[o] * msk;
+            }
+          }
+        } else if (QMODE == QM_SINGLE) {
+          visibility(qoff[m] + j * FT, pf[m][0], pf[m][1], pf[m][2], pf[m][3], pf[m][4], pf[m][5], pf[m][6]);
+        } else if (qoff[m] >= 0) {
+          visibility(qoff[m] + j * FT, pf[m][0], pf[m][1], pf[m][2], pf[m][3], pf[m][4], pf[m][5], pf[m][6]);
+          const int fg = (qoff[m] - q_b0[m] * p.nfp) + j * FT;
+          for (int n = 1; n < q_nb[m]; ++n) {
+            const int b = q_b0[m] + n;
+            const int o = b * p.nfp + fg;
+            const int o0 = p.bl_ant0[b] * p.nfp + fg, o1 = p.bl_ant1[b] * p.nfp + fg;
+            visibility(o, p.d_r[o], p.d_i[o], p.w[o], g_r[o0], g_i[o0], g_r[o1], g_i[o1]);
+          }
         }
-        qbuf[(s * NQ + 0) * FT + f] = qr;
-        qbuf[(s * NQ + 1) * FT + f] = qi;
+        qbuf[q_qb[m]] = qr;
+        qbuf[q_qb[m] + FT] = qi;
         if (SUM) {
-          qbuf[(s * NQ + 2) * FT + f] = pw;
-          qbuf[(s * NQ + 3) * FT + f] = qw;
+          qbuf[q_qb[m] + 2 * FT] = pw;
+          qbuf[q_qb[m] + 3 * FT] = qw;
         }
-        if (p.store_v) p.vout[(size_t)(it.slot0 + s) * p.nfp + fg] = make_float2(v_r, v_i);
+        if (p.store_v) p.vout[q_vo[m] + j * FT] = make_float2(v_r, v_i);
       }
     }
     if (j + 1 < p.ntiles) prefetch_q(j + 1);
