@@ -57,7 +57,6 @@ struct DevBuf {
 };
 
 static constexpr int RPT_DEFAULT = 11;  // steps per warp: 11 -> 45 KB tiles, 2 CTAs/SM (7 -> 3 CTAs/SM was measured slower)
-static constexpr int NWARP = 8;
 static constexpr int SMAX = 8;
 
 // ---- NCCL through dlopen (the library has no link-time dependency on it) -------------------------
@@ -104,7 +103,7 @@ using namespace calb2;
 
 struct calb2_plan {
   int device = 0, nants = 0, nf = 0, ngroups = 0;
-  int FL = 0, G = 0, FT = 0, KMAX = 0, nfp = 0, ntiles = 0, RPT = RPT_DEFAULT;
+  int FL = 0, G = 0, FT = 0, KMAX = 0, nfp = 0, ntiles = 0, RPT = RPT_DEFAULT, NW = 8;
   long long nbls = 0, nslots = 0, ncoef = 0, rows_total = 0, a_floats = 0, n_a_nz = 0;
   // host copies of the description
   std::vector<int> grp_ncomp, grp_nslots, grp_slot0, grp_coef0, slot_nbls, slot_grp, slot_row0, slot_bl0, slot_item,
@@ -115,6 +114,7 @@ struct calb2_plan {
   DevBuf<float> c_r, c_i, cm_r, cu_r, cm_i, cu_i, csnap_r, csnap_i, cgrad_r, cgrad_i, dcpart, hist, scratch_f;
   DevBuf<float2> z, y, vout;
   DevBuf<double> partials, red_d;
+  DevBuf<unsigned long long> dbg_out;
   DevBuf<ItemDesc> d_items;
   DevBuf<unsigned char> row_slot;
   DevBuf<int> row_coef, d_slot_row0, d_slot_bl0, d_bl_ant0, d_bl_ant1, d_bl_slot, ant_ptr, ant_ent, coef_row0, coef_grp, ant_partner,
@@ -157,7 +157,7 @@ static int dalloc(DevBuf<T>& buf, size_t n, calb2_plan* pl, bool zero = true) {
 }
 
 // Rows the greedy in-order packing would leave unused, as a fraction of the staged tile capacity.
-static double packing_fill(const calb2_plan_desc* d, int fl, int RPT) {
+static double packing_fill(const calb2_plan_desc* d, int fl, int RPT, int NWARP) {
   const int G = 32 / fl, kmax = NWARP * RPT * G;
   long long rows = 0, items = 0;
   int cur_rows = 0, cur_slots = 0;
@@ -180,7 +180,7 @@ static double packing_fill(const calb2_plan_desc* d, int fl, int RPT) {
 // Tile width: 64- and 32-channel tiles stream equally well, 16 is measurably worse (64-byte row segments), so
 // 16 is only used when a group's basis does not fit otherwise; between 64 and 32 the better-filled packing wins
 // (HERA-128: 0.77 vs 0.89 fill -> +10 % throughput at 32; HERA-37: 0.86 vs 0.43 -> 64).
-static int choose_fl(const calb2_plan_desc* d, int RPT, int* fl_out) {
+static int choose_fl(const calb2_plan_desc* d, int RPT, int NWARP, int* fl_out) {
   int maxc = 0;
   for (int g = 0; g < d->ngroups; ++g) maxc = std::max(maxc, d->group_ncomp[g]);
   auto fits = [&](int fl) {
@@ -197,7 +197,7 @@ static int choose_fl(const calb2_plan_desc* d, int RPT, int* fl_out) {
     return 0;
   }
   if (fits(16)) {
-    *fl_out = packing_fill(d, 8, RPT) > packing_fill(d, 16, RPT) + 0.02 ? 8 : 16;
+    *fl_out = packing_fill(d, 8, RPT, NWARP) > packing_fill(d, 16, RPT, NWARP) + 0.02 ? 8 : 16;
     return 0;
   }
   if (fits(8)) {
@@ -273,6 +273,11 @@ static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, in
   hp.store_v = store_v;
   hp.init_mode = init_mode;
   hp.fuse_update = 0;
+  {
+    static const int dbg = getenv("CALB2_DBG") ? atoi(getenv("CALB2_DBG")) : 0;
+    hp.dbg = dbg;
+    hp.dbg_out = pl->dbg_out.p;
+  }
   hp.c_r_rw = pl->c_r.p;
   hp.c_i_rw = pl->c_i.p;
   hp.cm_r = pl->cm_r.p;
@@ -596,9 +601,9 @@ const char* calb2_version(void) { return "calamity_b200 0.1 (sm_100a)"; }
 int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   if (!d || !out) return fail(CALB2_ERR_ARG, "null argument");
   if (d->nants <= 0 || d->nfreqs <= 0 || d->ngroups <= 0) return fail(CALB2_ERR_ARG, "empty problem");
-  const int rpt = RPT_DEFAULT;
+  const int rpt = RPT_DEFAULT, nwarp = 8;
   int fl = 0;
-  if (int r = choose_fl(d, rpt, &fl)) return r;
+  if (int r = choose_fl(d, rpt, nwarp, &fl)) return r;
   CU(cudaSetDevice(d->device));
   calb2_plan* pl = new calb2_plan();
   pl->device = d->device;
@@ -609,7 +614,8 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   pl->G = 32 / fl;
   pl->FT = 4 * fl;
   pl->RPT = rpt;
-  pl->KMAX = NWARP * rpt * pl->G;
+  pl->NW = nwarp;
+  pl->KMAX = nwarp * rpt * pl->G;
   pl->ntiles = (pl->nf + pl->FT - 1) / pl->FT;
   pl->nfp = pl->ntiles * pl->FT;
   const int G = pl->G;
@@ -802,6 +808,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(dalloc(pl->dcpart, (size_t)rows * 4, pl));
   TRY(dalloc(pl->partials, pl->items.size() * 4, pl));
   TRY(dalloc(pl->red_d, 4096, pl));
+  TRY(dalloc(pl->dbg_out, 16, pl));
   TRY(dalloc(pl->state, 1, pl));
   TRY(dalloc(pl->state_eval, 1, pl));
   TRY(dalloc(pl->comm_scalars, 4, pl));
@@ -837,6 +844,7 @@ int calb2_plan_destroy(calb2_plan* pl) {
   pl->vout.release();
   pl->partials.release();
   pl->red_d.release();
+  pl->dbg_out.release();
   pl->comm_scalars.release();
   pl->light_partials.release();
   pl->d_items.release();
@@ -1243,6 +1251,19 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
   cudaEventDestroy(ev_begin);
   cudaEventDestroy(ev_end);
 
+#ifdef CALB2_PROFILE
+  if (getenv("CALB2_DBG") && (atoi(getenv("CALB2_DBG")) & 128)) {
+    unsigned long long h[16];
+    cudaMemcpy(h, pl->dbg_out.p, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaMemset(pl->dbg_out.p, 0, sizeof(h));
+    const double nt = (double)h[15];
+    // BAR.SYNC is defer-blocking: the wait of the F barrier lands in "Q sums", that of the Q barrier in "load q", that of
+    // the B barrier in "issue"
+    fprintf(stderr, "[calb2 cycles per tile, thread 0] tile wait %.0f | F %.0f | Q sums %.0f  math+stores %.0f  prefetch %.0f | load q %.0f  B %.0f | issue %.0f",
+            h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[6] / nt, h[7] / nt);
+    fprintf(stderr, " (tiles %.0f)\n", nt);
+  }
+#endif
   res->nsteps_recorded = hs.nrec;
   res->nsteps_total = hs.step;
   res->final_loss = o->use_min ? hs.min_loss : hs.last_loss;

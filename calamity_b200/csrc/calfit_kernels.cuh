@@ -85,6 +85,8 @@ struct HeavyParams {
   // fused tail update (every group single-slot, no regulariser coupling): the item's own coefficients take
   // their optimizer step right after the backward sums are complete
   int fuse_update;
+  int dbg;                        // -DCALB2_PROFILE builds only: phase clocks / timing ablations (CALB2_DBG)
+  unsigned long long* dbg_out;    // [16] per-phase cycle sums of thread 0
   float* c_r_rw;
   float* c_i_rw;
   float* cm_r;
@@ -125,6 +127,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+
+// Development instrumentation, compiled only with -DCALB2_PROFILE (tools/build_prof.sh); the product library
+// carries none of it.  CALB2_TICK accumulates thread 0's clock64 per phase; CALB2_DEP makes the following tick wait
+// for a value (in-order issue).  Note that BAR.SYNC is "defer blocking": the wait of a barrier shows up at the first
+// dependent shared-memory access after it, not at the barrier.
+#ifdef CALB2_PROFILE
+#define CALB2_TICK(n)                \
+  if (prof) {                        \
+    const long long now = clock64(); \
+    tph[n] += now - tc;              \
+    tc = now;                        \
+  }
+#define CALB2_DEP(x) \
+  if (prof && (x) == 1.2345e-30f) tph[11] += 1;
+#define CALB2_PROF_BEGIN                                     \
+  const bool prof = (p.dbg & 128) && threadIdx.x == 0;      \
+  long long tph[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; \
+  long long tc = prof ? clock64() : 0;
+#define CALB2_PROF_END                                                                 \
+  if (prof) {                                                                          \
+    for (int n = 0; n < 12; ++n) atomicAdd(p.dbg_out + n, (unsigned long long)tph[n]); \
+    atomicAdd(p.dbg_out + 15, (unsigned long long)p.ntiles);                           \
+  }
+#else
+#define CALB2_TICK(n)
+#define CALB2_DEP(x)
+#define CALB2_PROF_BEGIN
+#define CALB2_PROF_END
+#endif
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc);
@@ -359,9 +390,11 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
   float loss_acc = 0.f, sr_acc = 0.f, si_acc = 0.f;
   const int row_off = (step_base * G + usub) * FT + fl * 4;  // this thread's float offset of step 0 in a tile
 
+  CALB2_PROF_BEGIN
   for (int j = 0; j < p.ntiles; ++j) {
     const int buf = j & 1;
     mbar_wait(&mbar[buf], (j >> 1) & 1);
+    CALB2_TICK(0)
     const float* Ab = Abuf + buf * C::TILE_FLOATS + row_off;
     const float2* cb = cbuf + step_base * G + usub;
 
@@ -412,6 +445,7 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
         flush(warp + cur);
       }
     }
+    CALB2_TICK(1)
     __syncthreads();
 
     // ---------------- phase Q: gains, model, residual, chi^2, dL/dv ----------------
@@ -426,6 +460,8 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
             v_i += vpart[q_vp[m] + w * 2 * FT + FT];
           }
         }
+        CALB2_DEP(v_r + v_i)
+        CALB2_TICK(2)
         float qr = 0.f, qi = 0.f, pw = 0.f, qw = 0.f;
         // one visibility: model = g_i conj(g_j) v, weighted residual, chi^2, z, dL/dv (calibration.py:1593-1609)
         auto visibility = [&](int o, float dr, float di, float w, float gr0, float gi0, float gr1, float gi1) {
@@ -480,7 +516,9 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
         if (p.store_v) p.vout[q_vo[m] + j * FT] = make_float2(v_r, v_i);
       }
     }
+    CALB2_TICK(3)
     if (j + 1 < p.ntiles) prefetch_q(j + 1);
+    CALB2_TICK(4)
     __syncthreads();
 
     // ---------------- phase B: backward contraction, accumulated in registers ----------------
@@ -495,6 +533,8 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
         }
       };
       load_q(s_first);
+      CALB2_DEP(q0.x + q1.x)
+      CALB2_TICK(5)
       if (chg == 0u) {
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
@@ -523,13 +563,16 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
     }
     // All warps are done with the tile buffer: refill it with tile j + 2.  (Replacing this barrier by an mbarrier
     // "buffer empty" handshake that only thread 0 waits on was measured 23 % SLOWER: 151 vs 196 it/s at HERA-350.)
+    CALB2_TICK(6)
     __syncthreads();
     if (tid == 0 && j + 2 < p.ntiles) {
       mbar_expect_tx(&mbar[buf], tile_bytes);
       bulk_g2s(Abuf + buf * C::TILE_FLOATS, Abase + (size_t)(j + 2) * it.nrows * FT, tile_bytes, &mbar[buf]);
     }
+    CALB2_TICK(7)
   }
   __syncthreads();  // the epilogue reuses the tile buffers
+  CALB2_PROF_END
 
   // ---------------- item epilogue: lane reduction of the backward sums ----------------
   // The reduced sums are staged in shared memory (the tile buffers are free now) so that the write-out --
