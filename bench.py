@@ -179,8 +179,10 @@ def workload_config(args, prob, sizes, world):
                     f"per-baseline DPSS fit, single integration",
         "optimizer": "Adamax lr=1e-2", "model_regularization": args.reg, "n_d": sizes["n_d"], "n_a_nz": sizes["n_a_nz"],
         "n_c_nz": sizes["n_c_nz"], "b_iter_bytes": sizes["b_iter"],
-        "parallelism": "1 GPU" if world == 1 else f"baseline groups sharded over {world} GPUs, NCCL all-reduce of "
-                                                   f"the gain gradient per iteration",
+        "parallelism": "1 GPU" if world == 1 else (
+            f"baseline groups sharded over {world} GPUs; per iteration the gain gradient and 3 scalars are exchanged "
+            + ("through NVLink peer memory, reduced inside the update kernels (no collective call)"
+               if getattr(args, "comm", "peer") == "peer" else "with NCCL all-reduce")),
         "l2": "inputs larger than L2 (no flush)" if sizes["b_iter"] > 4 * 126e6 else "working set near L2 size; "
               "L2-resident workload, HBM fraction not meaningful",
     }
@@ -198,6 +200,8 @@ def main():
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--fuse", type=int, default=0)
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gain-gradient exchange fused into the update kernel over NVLink peer memory, or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-bls", type=int, default=384)
     ap.add_argument("--cpu-steps", type=int, default=6)
@@ -225,7 +229,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from calamity_b200 import synth
-    from calamity_b200.fitter import FitPlan, nccl_unique_id
+    from calamity_b200.fitter import FitPlan, comm_init_peer, nccl_unique_id
     from calamity_b200.sharding import make_shard
 
     t_setup = time.perf_counter()
@@ -234,7 +238,9 @@ def main():
     sizes = full.sizes()
     shard = make_shard(full, rank, world)
     plan = FitPlan(shard.layout, device=local_rank, tile_freqs=args.tile)
-    if world > 1:
+    if world > 1 and args.comm == "peer":
+        comm_init_peer(plan, rank, world)
+    elif world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))

@@ -102,6 +102,8 @@ _SIGNATURES = {
     "calb2_get_weights": (C.c_int, [C.c_void_p, _FP]),
     "calb2_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]),
     "calb2_comm_unique_id": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "calb2_comm_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "calb2_comm_peer_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

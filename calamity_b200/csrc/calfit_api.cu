@@ -115,6 +115,8 @@ struct calb2_plan {
   DevBuf<float2> z, y, vout;
   DevBuf<double> partials, red_d;
   DevBuf<unsigned long long> dbg_out;
+  std::vector<cudaEvent_t> stage_ev;  // -DCALB2_PROFILE + CALB2_DBG&1024: one event per stage boundary per step
+  size_t stage_cursor = 0;
   DevBuf<ItemDesc> d_items;
   DevBuf<unsigned char> row_slot;
   DevBuf<int> row_coef, d_slot_row0, d_slot_bl0, d_bl_ant0, d_bl_ant1, d_bl_slot, ant_ptr, ant_ent, coef_row0, coef_grp, ant_partner,
@@ -136,6 +138,11 @@ struct calb2_plan {
   void* comm = nullptr;
   int rank = 0, nranks = 1;
   DevBuf<double> comm_scalars;
+  // peer-memory exchange (calb2_comm_peer_*): own buffer + the peers' buffers opened through cudaIpc
+  unsigned char* xbuf = nullptr;
+  void* xpeer[CALB2_MAX_RANKS] = {nullptr};
+  PeerView peers{};
+  unsigned int xseq = 0;  // steps enqueued so far on the exchange (identical on all ranks)
   size_t device_bytes = 0;
 };
 
@@ -315,6 +322,7 @@ static GainsParams gains_params(calb2_plan* pl, const FitState* st, const FitCon
   gp.mode = mode;
   gp.sum = sum ? 1 : 0;
   gp.eval = eval;
+  gp.peers.n = 0;
   return gp;
 }
 
@@ -417,6 +425,14 @@ static int all_reduce(calb2_plan* pl, void* buf, size_t count, int dtype) {
 }
 
 // One optimizer iteration (calibration.py:663-668) enqueued on the plan's stream.
+#ifdef CALB2_PROFILE
+#define CALB2_STAGE() \
+  if (pl->stage_cursor < pl->stage_ev.size()) cudaEventRecord(pl->stage_ev[pl->stage_cursor++], pl->stream);
+#else
+#define CALB2_STAGE()
+#endif
+static constexpr int NSTAGE = 8;  // boundaries per step: start, heavy, partials, gains-reduce, all-reduce, finalize, gains, coeffs
+
 static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freeze, bool want_fuse, float* hist,
                         cudaEvent_t ev0, cudaEvent_t ev1, long long* launches) {
   // coefficients can take their optimizer step in the heavy kernel's tail when nothing couples the groups
@@ -424,6 +440,7 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
   int npartials = (int)pl->items.size();
   const double* partials = pl->partials.p;
   if (ev0) CU(cudaEventRecord(ev0, pl->stream));
+  CALB2_STAGE()
   if (freeze) {  // the model is fixed: elementwise pass over the visibilities only
     LightParams lp{};
     lp.vout = pl->vout.p;
@@ -455,50 +472,111 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     CU(launch_heavy(pl, sum, hp, (int)pl->items.size(), pl->stream));
   }
   if (ev1) CU(cudaEventRecord(ev1, pl->stream));
+  CALB2_STAGE()
   FinalizeParams fp{};
   fp.st = pl->state.p;
   fp.k = k;
   fp.hist = hist;
   fp.eval_only = 0;
-  dim3 ggrid((pl->nfp / 2 + 127) / 128, pl->nants);
+  fp.peers.n = 0;
+  fp.xwait = 0;
+  fp.xpar = 0;
+  dim3 ggrid(pl->nants, (pl->nfp + GK_CH - 1) / GK_CH);
   const size_t ngrad = (size_t)2 * pl->nants * pl->nfp;
-  if (pl->nranks > 1) {
+  if (pl->nranks > 1 && pl->peers.n > 1) {
+    // ---- exchange through peer memory (NVLink): no collective library call in the loop ----
+    const unsigned int seq = pl->xseq++;
+    const int par = (int)(seq & 1u);
+    unsigned int* my_flag = reinterpret_cast<unsigned int*>(pl->xbuf);
+    double* my_scal = reinterpret_cast<double*>(pl->xbuf + XBUF_FLAG_BYTES) + par * 4;
+    float* my_grad = reinterpret_cast<float*>(pl->xbuf + XBUF_FLAG_BYTES + XBUF_SCAL_BYTES) + (size_t)par * ngrad;
+    reduce_partials_kernel<<<1, 1024, 0, pl->stream>>>(partials, npartials, my_scal);
+    CU(cudaGetLastError());
+    CALB2_STAGE()
+    fp.partials = nullptr;
+    fp.nitems = 0;
+    fp.peers = pl->peers;
+    fp.xpar = par;
+    GainsParams gred = gains_params(pl, pl->state.p, k, sum ? 1 : 4, sum, 0);
+    gred.grad_r = my_grad;
+    gred.grad_i = my_grad + ngrad / 2;
+    GainsParams gupd = gains_params(pl, pl->state.p, k, 2, sum, 0);
+    gupd.peers = pl->peers;
+    gupd.xpar = par;
+    if (!sum) {
+      // the local gradient partial does not need finalize's alpha / beta: publish scalars and gradient together
+      gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gred);
+      CU(cudaGetLastError());
+      CALB2_STAGE()
+      xpublish_kernel<<<1, 1, 0, pl->stream>>>(my_flag, 2u * seq + 2u);
+      CU(cudaGetLastError());
+      fp.xwait = 2u * seq + 2u;
+      CALB2_STAGE()
+      finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
+      CU(cudaGetLastError());
+      CALB2_STAGE()
+      *launches += 2;
+    } else {
+      // 'sum' regulariser: alpha / beta need the global sums first (two publish / wait rounds per step)
+      xpublish_kernel<<<1, 1, 0, pl->stream>>>(my_flag, 2u * seq + 1u);
+      CU(cudaGetLastError());
+      fp.xwait = 2u * seq + 1u;
+      finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
+      CU(cudaGetLastError());
+      gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gred);
+      CU(cudaGetLastError());
+      xpublish_kernel<<<1, 1, 0, pl->stream>>>(my_flag, 2u * seq + 2u);
+      CU(cudaGetLastError());
+      xwait_kernel<<<1, 32, 0, pl->stream>>>(pl->peers, 2u * seq + 2u, pl->state.p, 0);
+      CU(cudaGetLastError());
+      *launches += 4;
+    }
+    gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gupd);
+    CU(cudaGetLastError());
+    CALB2_STAGE()
+    *launches += 1;
+  } else if (pl->nranks > 1) {
     reduce_partials_kernel<<<1, 1024, 0, pl->stream>>>(partials, npartials, pl->comm_scalars.p);
     CU(cudaGetLastError());
     *launches += 1;
+    CALB2_STAGE()
     fp.partials = pl->comm_scalars.p;
     fp.nitems = 1;
     if (!sum && g_nccl.GroupStart && g_nccl.GroupEnd) {
       // without the regulariser the gain-gradient reduce does not need finalize's alpha/beta: reduce first and
       // send scalars + gradient tables in ONE grouped NCCL launch
-      gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 4, sum, 0));
+      gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 4, sum, 0));
       CU(cudaGetLastError());
+      CALB2_STAGE()
       g_nccl.GroupStart();
       int r1 = all_reduce(pl, pl->comm_scalars.p, 4, NCCL_FLOAT64);
       int r2 = all_reduce(pl, pl->ggrad_r.p, ngrad, NCCL_FLOAT32);
       g_nccl.GroupEnd();
       if (r1) return r1;
       if (r2) return r2;
+      CALB2_STAGE()
       finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
       CU(cudaGetLastError());
+      CALB2_STAGE()
     } else {
       if (int r = all_reduce(pl, pl->comm_scalars.p, 4, NCCL_FLOAT64)) return r;
       finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
       CU(cudaGetLastError());
-      gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 1, sum, 0));
+      gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 1, sum, 0));
       CU(cudaGetLastError());
       // real and imaginary gradient tables are adjacent halves of one allocation
       if (int r = all_reduce(pl, pl->ggrad_r.p, ngrad, NCCL_FLOAT32)) return r;
     }
-    gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 2, sum, 0));
+    gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 2, sum, 0));
     CU(cudaGetLastError());
+    CALB2_STAGE()
     *launches += 1;
   } else {
     fp.partials = partials;
     fp.nitems = npartials;
     finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
     CU(cudaGetLastError());
-    gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 0, sum, 0));
+    gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 0, sum, 0));
     CU(cudaGetLastError());
   }
   if ((!freeze && !fuse) || (k.use_min && !freeze)) {
@@ -508,6 +586,7 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     CU(cudaGetLastError());
     *launches += 1;
   }
+  CALB2_STAGE()
   *launches += 3;
   return 0;
 }
@@ -833,6 +912,9 @@ int calb2_plan_destroy(calb2_plan* pl) {
   cudaSetDevice(pl->device);
   if (pl->stream) cudaStreamSynchronize(pl->stream);
   if (pl->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pl->comm);
+  for (int r = 0; r < CALB2_MAX_RANKS; ++r)
+    if (pl->xpeer[r]) cudaIpcCloseMemHandle(pl->xpeer[r]);
+  if (pl->xbuf) cudaFree(pl->xbuf);
   DevBuf<float>* fb[] = {&pl->A, &pl->d_r, &pl->d_i, &pl->w, &pl->g_r[0], &pl->g_r[1], &pl->g_i[0], &pl->g_i[1],
                          &pl->gm_r, &pl->gu_r, &pl->gm_i, &pl->gu_i, &pl->gsnap_r, &pl->gsnap_i, &pl->ggrad_r,
                          &pl->ggrad_i, &pl->c_r, &pl->c_i, &pl->cm_r, &pl->cu_r, &pl->cm_i, &pl->cu_i, &pl->csnap_r,
@@ -1094,10 +1176,13 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, 
   fp.st = pl->state_eval.p;
   fp.k = k;
   fp.eval_only = 1;
+  fp.peers.n = 0;
+  fp.xwait = 0;
+  fp.xpar = 0;
   finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
   CU(cudaGetLastError());
-  dim3 ggrid((pl->nfp / 2 + 127) / 128, pl->nants);
-  gains_kernel<<<ggrid, 128, 0, pl->stream>>>(gains_params(pl, pl->state_eval.p, k, 1, sum, 1));
+  dim3 ggrid(pl->nants, (pl->nfp + GK_CH - 1) / GK_CH);
+  gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state_eval.p, k, 1, sum, 1));
   CU(cudaGetLastError());
   coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(coeff_params(pl, pl->state_eval.p, k, 1, sum));
   CU(cudaGetLastError());
@@ -1165,6 +1250,13 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
     }
     if (int r = run_forward_store_v(pl)) return r;  // v = sum_k c_k A_k, once: the coefficients are frozen
   }
+#ifdef CALB2_PROFILE
+  if (getenv("CALB2_DBG") && (atoi(getenv("CALB2_DBG")) & 1024) && pl->nranks > 1 && !sum) {
+    pl->stage_ev.resize((size_t)total * NSTAGE);
+    for (auto& e : pl->stage_ev) cudaEventCreate(&e);
+    pl->stage_cursor = 0;
+  }
+#endif
   FitState s0{};
   s0.step = 0;
   s0.stop_after = (int)(total - 1);
@@ -1252,6 +1344,22 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
   cudaEventDestroy(ev_end);
 
 #ifdef CALB2_PROFILE
+  if (!pl->stage_ev.empty()) {
+    const char* names[NSTAGE - 1] = {"heavy", "partials", "gains-reduce", "nccl", "finalize", "gains-update", "coeffs"};
+    double sum_ms[NSTAGE - 1] = {0};
+    const size_t nsteps_done = pl->stage_cursor / NSTAGE;
+    for (size_t st = 0; st < nsteps_done; ++st)
+      for (int n = 0; n + 1 < NSTAGE; ++n) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pl->stage_ev[st * NSTAGE + n], pl->stage_ev[st * NSTAGE + n + 1]);
+        sum_ms[n] += ms;
+      }
+    fprintf(stderr, "[calb2 stage us/step, rank %d]", pl->rank);
+    for (int n = 0; n + 1 < NSTAGE; ++n) fprintf(stderr, " %s %.1f", names[n], 1e3 * sum_ms[n] / (double)nsteps_done);
+    fprintf(stderr, "\n");
+    for (auto& e : pl->stage_ev) cudaEventDestroy(e);
+    pl->stage_ev.clear();
+  }
   if (getenv("CALB2_DBG") && (atoi(getenv("CALB2_DBG")) & 128)) {
     unsigned long long h[16];
     cudaMemcpy(h, pl->dbg_out.p, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1303,6 +1411,52 @@ int calb2_comm_init(calb2_plan* pl, const void* id, int32_t rank, int32_t nranks
   CU(cudaMemset(pl->ggrad_r.p, 0, 2 * ng * sizeof(float)));
   pl->ggrad_i.p = pl->ggrad_r.p + ng;  // view; never released separately
   pl->ggrad_i.n = 0;
+  return 0;
+}
+
+static size_t xbuf_bytes(const calb2_plan* pl) {
+  return (size_t)XBUF_FLAG_BYTES + XBUF_SCAL_BYTES + (size_t)2 * 2 * pl->nants * pl->nfp * sizeof(float);
+}
+
+int calb2_comm_peer_export(calb2_plan* pl, void* ipc_handle_out) {
+  if (!pl || !ipc_handle_out) return fail(CALB2_ERR_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  CU(cudaSetDevice(pl->device));
+  if (!pl->xbuf) {
+    CU(cudaMalloc(&pl->xbuf, xbuf_bytes(pl)));
+    CU(cudaMemset(pl->xbuf, 0, xbuf_bytes(pl)));
+    CU(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, pl->xbuf));
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int calb2_comm_peer_import(calb2_plan* pl, const void* ipc_handles, int32_t rank, int32_t nranks) {
+  if (!pl || !ipc_handles) return fail(CALB2_ERR_ARG, "null argument");
+  if (nranks < 1 || nranks > CALB2_MAX_RANKS || rank < 0 || rank >= nranks) return fail(CALB2_ERR_ARG, "bad rank/nranks");
+  if (!pl->xbuf) return fail(CALB2_ERR_STATE, "calb2_comm_peer_export first");
+  CU(cudaSetDevice(pl->device));
+  pl->rank = rank;
+  pl->nranks = nranks;
+  pl->peers.n = nranks;
+  const size_t ngrad_off = (size_t)XBUF_FLAG_BYTES + XBUF_SCAL_BYTES;
+  for (int r = 0; r < nranks; ++r) {
+    unsigned char* base = pl->xbuf;
+    if (r != rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)ipc_handles + (size_t)r * sizeof(h), sizeof(h));
+      void* ptr = nullptr;
+      CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      pl->xpeer[r] = ptr;
+      base = (unsigned char*)ptr;
+    }
+    pl->peers.flag[r] = reinterpret_cast<const unsigned int*>(base);
+    pl->peers.scal[r] = reinterpret_cast<const double*>(base + XBUF_FLAG_BYTES);
+    pl->peers.grad[r] = reinterpret_cast<const float*>(base + ngrad_off);
+  }
+  pl->xseq = 0;
   return 0;
 }
 

@@ -56,6 +56,47 @@ struct FitConsts {
   int n_skip;        // n_profile_steps + 1 unrecorded steps
 };
 
+// Peer-memory exchange between the ranks of one node (one process per GPU; buffers shared with cudaIpc).  Every rank
+// owns ONE exchange buffer: [flag | scalars[2][4] | gain-gradient partials[2][2 nants nfp]], double-buffered by the
+// parity of a step sequence number.  A rank publishes its partials of step `seq` by storing seq + 1 to its flag with
+// release.sys; consumers poll all flags with acquire.sys and then read every rank's partial straight from the
+// owner's memory over NVLink, adding them in rank order -- deterministic and bit-identical on all ranks.
+constexpr int CALB2_MAX_RANKS = 16;
+constexpr int XBUF_FLAG_BYTES = 128;
+constexpr int XBUF_SCAL_BYTES = 128;  // double [2][4] + pad
+struct PeerView {
+  const unsigned int* flag[CALB2_MAX_RANKS];
+  const double* scal[CALB2_MAX_RANKS];  // [2][4]
+  const float* grad[CALB2_MAX_RANKS];   // [2][2 * nants * nfp]
+  int n;                                // ranks, 0 or 1: no exchange
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// the partials written by the preceding kernels of this stream become visible to the peers, then the flag moves
+__global__ void xpublish_kernel(unsigned int* flag, unsigned int value) {
+  __threadfence_system();
+  st_release_sys(flag, value);
+}
+// one lane per rank waits until that rank has published step `value`
+__device__ __forceinline__ void xwait_all(const PeerView& pv, unsigned int value) {
+  if ((int)threadIdx.x < pv.n) {
+    while ((int)(ld_acquire_sys(pv.flag[threadIdx.x]) - value) < 0) {
+    }
+  }
+  __syncthreads();
+}
+__global__ void xwait_kernel(const PeerView pv, unsigned int value, const FitState* st, int before_finalize) {
+  if (before_finalize ? (st->step > st->stop_after) : !st->upd_active) return;
+  xwait_all(pv, value);
+}
+
 struct HeavyParams {
   const float* A;
   const ItemDesc* items;
@@ -657,6 +698,9 @@ struct FinalizeParams {
   FitConsts k;
   float* hist;
   int eval_only;  // 1: just publish loss / alpha / beta, no loop bookkeeping
+  PeerView peers; // peers.n > 1: wait until every rank's flag reached `xwait`, then add their scalars in rank order
+  unsigned int xwait;
+  int xpar;       // parity of the step sequence number (selects the half of the double-buffered partials)
 };
 
 __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams p) {
@@ -667,30 +711,42 @@ __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams 
     return;
   }
   double a = 0.0, b = 0.0, c = 0.0;
-  for (int i = threadIdx.x; i < p.nitems; i += blockDim.x) {
-    a += p.partials[(size_t)i * 4 + 0];
-    b += p.partials[(size_t)i * 4 + 1];
-    c += p.partials[(size_t)i * 4 + 2];
-  }
+  if (p.peers.n > 1) {
+    xwait_all(p.peers, p.xwait);
+    if (threadIdx.x != 0) return;
+    const int par = p.xpar;
+    for (int r = 0; r < p.peers.n; ++r) {  // rank order: identical sums on every rank
+      const volatile double* sc = p.peers.scal[r] + par * 4;
+      a += sc[0];
+      b += sc[1];
+      c += sc[2];
+    }
+  } else {
+    for (int i = threadIdx.x; i < p.nitems; i += blockDim.x) {
+      a += p.partials[(size_t)i * 4 + 0];
+      b += p.partials[(size_t)i * 4 + 1];
+      c += p.partials[(size_t)i * 4 + 2];
+    }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, off);
-    b += __shfl_xor_sync(0xffffffffu, b, off);
-    c += __shfl_xor_sync(0xffffffffu, c, off);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-    sh[0][warp] = a;
-    sh[1][warp] = b;
-    sh[2][warp] = c;
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  a = b = c = 0.0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-    a += sh[0][w];
-    b += sh[1][w];
-    c += sh[2][w];
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      b += __shfl_xor_sync(0xffffffffu, b, off);
+      c += __shfl_xor_sync(0xffffffffu, c, off);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+      sh[0][warp] = a;
+      sh[1][warp] = b;
+      sh[2][warp] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    a = b = c = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      a += sh[0][w];
+      b += sh[1][w];
+      c += sh[2][w];
+    }
   }
   float loss = (float)a;
   float alpha = 0.f, beta = 0.f;
@@ -754,10 +810,22 @@ struct GainsParams {
   int mode;             // 0: reduce + update; 1: reduce only -> grad; 2: update only from grad; 4: as 1, before finalize
   int sum;
   int eval;             // 1: stand-alone gradient evaluation (no step in flight)
+  PeerView peers;       // mode 2 with peers.n > 1: gradient = sum over ranks (rank order) of their published partials
+  int xpar;             // parity of the step sequence number
 };
 
-// Two adjacent channels per thread: z / y rows are read as float4 (two complex values), gain rows as float2.
-__global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
+// One CTA per (antenna, 64-channel block): 32 lanes along frequency (two adjacent channels each: z / y rows are read
+// as float4, gain rows as float2) x GK_EG entry groups.  Entry group g walks the antenna's baselines e0 + g,
+// e0 + g + GK_EG, ... with four loads in flight; the GK_EG partial sums are then added in a fixed order through
+// shared memory, so the result is deterministic and does not depend on the launch.  (The earlier one-thread-per-
+// channel version walked all 2 (Nant - 1) entries serially: 250 us at HERA-350, and just as long on every rank of a
+// multi-GPU run whose contiguous shard holds all baselines of a few antennas.)
+constexpr int GK_EG = 8;        // entry groups per CTA
+constexpr int GK_CH = 64;       // channels per CTA
+constexpr int GK_THREADS = 32 * GK_EG;
+
+__global__ void __launch_bounds__(GK_THREADS) gains_kernel(const GainsParams p) {
+  __shared__ float4 sh[GK_EG][32];
   const FitState* st = p.st;
   int src;
   if (p.eval) {
@@ -769,73 +837,115 @@ __global__ void __launch_bounds__(128) gains_kernel(const GainsParams p) {
     if (!st->upd_active) return;
     src = (st->step - 1) & 1;
   }
-  const int ant = blockIdx.y;
-  const int f = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  if (f >= p.nfp) return;  // nfp is a multiple of 16
+  // grid = (antennas, channel blocks), antennas fastest: the CTAs in flight share one 64-channel block, whose slice of z
+  // (nbls x 512 B = 31 MB at HERA-350) stays in L2 between its two reads (once per end of every baseline)
+  const int ant = blockIdx.x;
+  const int lane = threadIdx.x & 31, eg = threadIdx.x >> 5;
+  const int f = blockIdx.y * GK_CH + 2 * lane;
+  const bool f_ok = f < p.nfp;  // nfp is a multiple of 16, f is even
   const float* __restrict__ gr = p.g_r[src];
   const float* __restrict__ gi = p.g_i[src];
   const size_t o = (size_t)ant * p.nfp + f;
   float2 acc_r = make_float2(0.f, 0.f), acc_i = make_float2(0.f, 0.f);
   if (p.mode != 2) {
-    const float alpha = st->alpha, beta = st->beta;
-    const int e0 = p.ant_ptr[ant], e1 = p.ant_ptr[ant + 1];
-    auto one = [&](bool side1, float zx, float zy, float yx, float yy, float pr, float pi, float& ar, float& ai) {
-      if (p.sum) {
-        zx += alpha * yx + beta * yy;
-        zy += alpha * yy - beta * yx;
-      }
-      if (!side1) {  // this antenna is ant0: conj(z) * g_partner
-        ar += zx * pr + zy * pi;
-        ai += zx * pi - zy * pr;
-      } else {       // this antenna is ant1: z * g_partner
-        ar += zx * pr - zy * pi;
-        ai += zx * pi + zy * pr;
-      }
-    };
-    auto accumulate = [&](int ent, const float4& z, const float4& y, const float2& pr, const float2& pi) {
-      const bool side1 = (ent & 1) != 0;
-      one(side1, z.x, z.y, y.x, y.y, pr.x, pi.x, acc_r.x, acc_i.x);
-      one(side1, z.z, z.w, y.z, y.w, pr.y, pi.y, acc_r.y, acc_i.y);
-    };
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    constexpr int U = 8;  // independent loads in flight per thread; the summation order stays e0..e1-1
-    int e = e0;
-    for (; e + U <= e1; e += U) {
-      int ent[U], par[U];
-      float4 zz[U], yy[U];
-      float2 pr[U], pi[U];
+    if (f_ok) {
+      const float alpha = st->alpha, beta = st->beta;
+      const int e0 = p.ant_ptr[ant], e1 = p.ant_ptr[ant + 1];
+      auto one = [&](bool side1, float zx, float zy, float yx, float yy, float pr, float pi, float& ar, float& ai) {
+        if (p.sum) {
+          zx += alpha * yx + beta * yy;
+          zy += alpha * yy - beta * yx;
+        }
+        if (!side1) {  // this antenna is ant0: conj(z) * g_partner
+          ar += zx * pr + zy * pi;
+          ai += zx * pi - zy * pr;
+        } else {       // this antenna is ant1: z * g_partner
+          ar += zx * pr - zy * pi;
+          ai += zx * pi + zy * pr;
+        }
+      };
+      auto accumulate = [&](int ent, const float4& z, const float4& y, const float2& pr, const float2& pi) {
+        const bool side1 = (ent & 1) != 0;
+        one(side1, z.x, z.y, y.x, y.y, pr.x, pi.x, acc_r.x, acc_i.x);
+        one(side1, z.z, z.w, y.z, y.w, pr.y, pi.y, acc_r.y, acc_i.y);
+      };
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      constexpr int U = 4;  // independent loads in flight per thread; the group's order stays ascending
+      int e = e0 + eg;
+      for (; e + (U - 1) * GK_EG < e1; e += U * GK_EG) {
+        int ent[U], par[U];
+        float4 zz[U], yy[U];
+        float2 pr[U], pi[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        ent[k] = p.ant_ent[e + k];
-        par[k] = p.ant_partner[e + k];
-      }
+        for (int k = 0; k < U; ++k) {
+          ent[k] = p.ant_ent[e + k * GK_EG];
+          par[k] = p.ant_partner[e + k * GK_EG];
+        }
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const size_t ob = (size_t)(ent[k] >> 1) * p.nfp + f;
-        const size_t op = (size_t)par[k] * p.nfp + f;
-        zz[k] = *reinterpret_cast<const float4*>(p.z + ob);
-        yy[k] = p.sum ? *reinterpret_cast<const float4*>(p.y + ob) : zero4;
-        pr[k] = *reinterpret_cast<const float2*>(gr + op);
-        pi[k] = *reinterpret_cast<const float2*>(gi + op);
-      }
+        for (int k = 0; k < U; ++k) {
+          const size_t ob = (size_t)(ent[k] >> 1) * p.nfp + f;
+          const size_t op = (size_t)par[k] * p.nfp + f;
+          zz[k] = *reinterpret_cast<const float4*>(p.z + ob);
+          yy[k] = p.sum ? *reinterpret_cast<const float4*>(p.y + ob) : zero4;
+          pr[k] = *reinterpret_cast<const float2*>(gr + op);
+          pi[k] = *reinterpret_cast<const float2*>(gi + op);
+        }
 #pragma unroll
-      for (int k = 0; k < U; ++k) accumulate(ent[k], zz[k], yy[k], pr[k], pi[k]);
+        for (int k = 0; k < U; ++k) accumulate(ent[k], zz[k], yy[k], pr[k], pi[k]);
+      }
+      for (; e < e1; e += GK_EG) {
+        const int ent = p.ant_ent[e];
+        const size_t ob = (size_t)(ent >> 1) * p.nfp + f;
+        const size_t op = (size_t)p.ant_partner[e] * p.nfp + f;
+        accumulate(ent, *reinterpret_cast<const float4*>(p.z + ob), p.sum ? *reinterpret_cast<const float4*>(p.y + ob) : zero4,
+                   *reinterpret_cast<const float2*>(gr + op), *reinterpret_cast<const float2*>(gi + op));
+      }
     }
-    for (; e < e1; ++e) {
-      const int ent = p.ant_ent[e];
-      const size_t ob = (size_t)(ent >> 1) * p.nfp + f;
-      const size_t op = (size_t)p.ant_partner[e] * p.nfp + f;
-      accumulate(ent, *reinterpret_cast<const float4*>(p.z + ob), p.sum ? *reinterpret_cast<const float4*>(p.y + ob) : zero4,
-                 *reinterpret_cast<const float2*>(gr + op), *reinterpret_cast<const float2*>(gi + op));
+    sh[eg][lane] = make_float4(acc_r.x, acc_r.y, acc_i.x, acc_i.y);
+    __syncthreads();
+    if (eg != 0 || !f_ok) return;
+    float4 t = sh[0][lane];
+#pragma unroll
+    for (int g = 1; g < GK_EG; ++g) {  // fixed order
+      const float4 u = sh[g][lane];
+      t.x += u.x;
+      t.y += u.y;
+      t.z += u.z;
+      t.w += u.w;
     }
+    acc_r = make_float2(t.x, t.y);
+    acc_i = make_float2(t.z, t.w);
     if (p.grad_r) {
       *reinterpret_cast<float2*>(p.grad_r + o) = acc_r;
       *reinterpret_cast<float2*>(p.grad_i + o) = acc_i;
     }
     if (p.mode == 1 || p.mode == 4) return;
   } else {
-    acc_r = *reinterpret_cast<const float2*>(p.grad_r + o);
-    acc_i = *reinterpret_cast<const float2*>(p.grad_i + o);
+    if (eg != 0 || !f_ok) return;
+    if (p.peers.n > 1) {  // fused all-reduce: every rank's partial straight from its owner's memory, fixed order
+      const size_t ng = (size_t)p.nants * p.nfp;
+      float2 tr[CALB2_MAX_RANKS], ti[CALB2_MAX_RANKS];
+#pragma unroll
+      for (int r = 0; r < CALB2_MAX_RANKS; ++r) {
+        if (r < p.peers.n) {
+          const float* base = p.peers.grad[r] + (size_t)p.xpar * 2 * ng + o;
+          tr[r] = __ldcv(reinterpret_cast<const float2*>(base));
+          ti[r] = __ldcv(reinterpret_cast<const float2*>(base + ng));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < CALB2_MAX_RANKS; ++r) {
+        if (r < p.peers.n) {
+          acc_r.x += tr[r].x;
+          acc_r.y += tr[r].y;
+          acc_i.x += ti[r].x;
+          acc_i.y += ti[r].y;
+        }
+      }
+    } else {
+      acc_r = *reinterpret_cast<const float2*>(p.grad_r + o);
+      acc_i = *reinterpret_cast<const float2*>(p.grad_i + o);
+    }
   }
   const float lr_t = st->lr_t;
   const float a_r[2] = {acc_r.x, acc_r.y}, a_i[2] = {acc_i.x, acc_i.y};

@@ -160,6 +160,34 @@ class FitPlan:
         nat.check(self._lib.calb2_comm_init(self._handle, C.cast(buf, C.c_void_p), rank, nranks, nat.find_nccl().encode()))
 
 
+    def peer_export(self):
+        """64-byte cudaIpc handle of this rank's exchange buffer (to be all-gathered by the caller)."""
+        buf = (C.c_char * 64)()
+        nat.check(self._lib.calb2_comm_peer_export(self._handle, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def peer_import(self, handles, rank, nranks):
+        """`handles`: the exported handles of all ranks, concatenated in rank order (64 bytes each)."""
+        blob = bytes(handles)
+        assert len(blob) == 64 * nranks, len(blob)
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        nat.check(self._lib.calb2_comm_peer_import(self._handle, C.cast(buf, C.c_void_p), rank, nranks))
+
+
+def comm_init_peer(plan, rank, world):
+    """Set up the NVLink peer-memory exchange with torch.distributed (any backend) as the out-of-band channel."""
+    import torch
+    import torch.distributed as dist
+
+    mine = torch.frombuffer(bytearray(plan.peer_export()), dtype=torch.uint8)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = mine.to(dev)
+    allh = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    plan.peer_import(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh), rank, world)
+    dist.barrier()
+
+
 def nccl_unique_id():
     buf = (C.c_char * 128)()
     nat.check(nat.load().calb2_comm_unique_id(C.cast(buf, C.c_void_p), nat.find_nccl().encode()))

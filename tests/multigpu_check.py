@@ -23,23 +23,27 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from calamity_b200 import synth
-    from calamity_b200.fitter import FitPlan, nccl_unique_id
+    from calamity_b200.fitter import FitPlan, comm_init_peer, nccl_unique_id
     from calamity_b200.sharding import make_shard
 
     workload = sys.argv[1] if len(sys.argv) > 1 else "hera37"
     reg = sys.argv[2] if len(sys.argv) > 2 else "none"
+    comm = sys.argv[3] if len(sys.argv) > 3 else "peer"
     prob = synth.make(workload, init_gain_scatter=0.02, coeff_error=0.05)
     full = prob.layout()
     shard = make_shard(full, rank, world)
     log("shard groups", shard.g0, shard.g1)
     plan = FitPlan(shard.layout, device=local)
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    log("got id")
-    plan.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
-    log("comm ok")
+    if comm == "peer":  # NVLink peer-memory exchange fused into the update kernels
+        comm_init_peer(plan, rank, world)
+    else:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        log("got id")
+        plan.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    log("comm ok", comm)
     plan.set_integration(*(shard.take_baselines(x) for x in (prob.data_r, prob.data_i, prob.wgts)))
     plan.set_gains(prob.g0_r, prob.g0_i)
     plan.set_coeffs(shard.take_coeffs(prob.c0_r), shard.take_coeffs(prob.c0_i))
@@ -63,7 +67,7 @@ def main():
         err = float(np.max(np.abs(hist.astype(np.float64) - h1) / h1))
         gerr = float(np.max(np.abs(g_r - g1)) / np.max(np.abs(g1)))
         ok = err < 1e-5 and gerr < 1e-4
-        print(f"{'PASS' if ok else 'FAIL'} world={world} {workload} reg={reg} loss_rel_err={err:.2e} gain_rel_err={gerr:.2e} "
+        print(f"{'PASS' if ok else 'FAIL'} world={world} {workload} reg={reg} comm={comm} loss_rel_err={err:.2e} gain_rel_err={gerr:.2e} "
               f"launches={res['kernel_launches']}", flush=True)
     # every rank must hold identical gains (replicated state)
     t = torch.from_numpy(g_r.copy()).cuda()

@@ -1,4 +1,5 @@
-"""GPU (>= 2 devices): baseline-group sharding with the in-loop NCCL all-reduce reproduces the single-GPU fit.
+"""GPU (>= 2 devices): baseline-group sharding reproduces the single-GPU fit, with the per-iteration exchange done
+either through NVLink peer memory (fused into the update kernels) or with the in-loop NCCL all-reduce.
 Skipped on single-GPU boxes; the same data flow is covered on CPU by tests/test_cpu_sharding_gloo.py."""
 import os
 import socket
@@ -11,8 +12,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("comm", ["peer", "nccl"])
 @pytest.mark.parametrize("reg", ["none", "sum"])
-def test_sharded_fit_matches_single_gpu(native_built, reg):
+def test_sharded_fit_matches_single_gpu(native_built, reg, comm):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -21,6 +23,6 @@ def test_sharded_fit_matches_single_gpu(native_built, reg):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "multigpu_check.py"), "hera37", reg]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multigpu_check.py"), "hera37", reg, comm]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0 and "PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
