@@ -49,6 +49,13 @@ class FitOptions(C.Structure):
         ("steps_per_sync", C.c_int32),
         ("use_graph", C.c_int32),
         ("fuse_tail_update", C.c_int32),
+        ("rho", C.c_float),
+        ("momentum", C.c_float),
+        ("initial_accumulator_value", C.c_float),
+        ("l1_regularization_strength", C.c_float),
+        ("l2_regularization_strength", C.c_float),
+        ("learning_rate_power", C.c_float),
+        ("nesterov", C.c_int32),
     ]
 
 

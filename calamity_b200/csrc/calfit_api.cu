@@ -436,7 +436,7 @@ static constexpr int NSTAGE = 8;  // boundaries per step: start, heavy, partials
 static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freeze, bool want_fuse, float* hist,
                         cudaEvent_t ev0, cudaEvent_t ev1, long long* launches) {
   // coefficients can take their optimizer step in the heavy kernel's tail when nothing couples the groups
-  const bool fuse = want_fuse && !sum && !freeze && pl->all_single_slot;
+  const bool fuse = want_fuse && !sum && !freeze && pl->all_single_slot && k.optimizer <= CALB2_OPT_SGD && k.momentum == 0.f;
   int npartials = (int)pl->items.size();
   const double* partials = pl->partials.p;
   if (ev0) CU(cudaEventRecord(ev0, pl->stream));
@@ -1201,7 +1201,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, 
 int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, calb2_fit_result* res) {
   if (!pl || !o || !res) return fail(CALB2_ERR_ARG, "null argument");
   if (!pl->have_data || !pl->have_gains || !pl->have_coeffs) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
-  if (o->optimizer < 0 || o->optimizer > 2) return fail(CALB2_ERR_ARG, "unknown optimizer id %d", o->optimizer);
+  if (o->optimizer < 0 || o->optimizer > CALB2_OPT_FTRL) return fail(CALB2_ERR_ARG, "unknown optimizer id %d", o->optimizer);
   if (o->maxsteps < 0 || o->n_profile_steps < 0) return fail(CALB2_ERR_ARG, "negative step count");
   if (o->maxsteps > 0 && !loss_history) return fail(CALB2_ERR_ARG, "loss_history is null");
   CU(cudaSetDevice(pl->device));
@@ -1219,6 +1219,13 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
   k.beta1 = o->beta_1;
   k.beta2 = o->beta_2;
   k.eps = o->epsilon;
+  k.rho = o->rho;
+  k.momentum = o->momentum;
+  k.init_acc = o->initial_accumulator_value;
+  k.l1 = o->l1_regularization_strength;
+  k.l2 = o->l2_regularization_strength;
+  k.lr_power = o->learning_rate_power;
+  k.nesterov = o->nesterov;
   k.maxsteps = o->maxsteps;
   k.tol = o->tol;
   k.use_min = o->use_min;
@@ -1238,6 +1245,15 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
   // fresh optimizer per integration (calibration.py:571): zero slots and step counter
   DevBuf<float>* slots[] = {&pl->gm_r, &pl->gu_r, &pl->gm_i, &pl->gu_i, &pl->cm_r, &pl->cu_r, &pl->cm_i, &pl->cu_i};
   for (auto* s : slots) CU(cudaMemsetAsync(s->p, 0, s->bytes(), pl->stream));
+  // accumulators that start at initial_accumulator_value: Adagrad keeps it in slot u, Ftrl in slot m
+  if (k.optimizer == CALB2_OPT_ADAGRAD || k.optimizer == CALB2_OPT_FTRL) {
+    DevBuf<float>* acc_u[] = {&pl->gu_r, &pl->gu_i, &pl->cu_r, &pl->cu_i};
+    DevBuf<float>* acc_m[] = {&pl->gm_r, &pl->gm_i, &pl->cm_r, &pl->cm_i};
+    for (auto* s : (k.optimizer == CALB2_OPT_ADAGRAD ? acc_u : acc_m)) {
+      if (s->n) fill_kernel<<<256, 256, 0, pl->stream>>>(s->p, s->n, k.init_acc);
+      CU(cudaGetLastError());
+    }
+  }
   if (pl->hist.n < (size_t)std::max(1, o->maxsteps)) {
     if (int r = dalloc(pl->hist, (size_t)std::max(1, o->maxsteps), pl)) return r;
   }

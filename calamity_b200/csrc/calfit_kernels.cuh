@@ -41,13 +41,18 @@ struct FitState {
   float alpha;       // 2 (S_r - P_r)   (d/dS of the 'sum' regulariser, calibration.py:1654)
   float beta;        // 2 (S_i - P_i)
   float lr_t;        // bias-corrected step size of the update in flight
+  float aux[4];      // per-step optimizer scalars (Nadam: 1 - m_schedule_new, 1 - m_schedule_next, 1 - u_t, u_{t+1}; and aux2[0] below)
+  float aux2[2];     // Nadam: 1 - beta_2^t; spare
+  double m_schedule; // Nadam: running product of the momentum schedule (Keras `_m_cache`)
   float s_r, s_i;
   double chi2;
 };
 
 struct FitConsts {
-  int optimizer;
+  int optimizer;     // CALB2_OPT_*
   float lr, beta1, beta2, eps;
+  float rho, momentum, init_acc, l1, l2, lr_power;  // RMSprop / Adadelta / SGD / Adagrad / Ftrl (Keras names)
+  int nesterov;
   int maxsteps;
   double tol;
   int use_min;
@@ -216,27 +221,73 @@ __device__ __forceinline__ void axpy4(float c, const float4& a, float4& v) {
 // optimizer rules (Keras OptimizerV2; see oracle/restatement.py for provenance)
 //   SPARSE = the IndexedSlices form used for the gains, dense form for the coefficients
 // ------------------------------------------------------------------------------------------------
+enum { OPT_ADAMAX = 0, OPT_ADAM = 1, OPT_SGD = 2, OPT_RMSPROP = 3, OPT_ADAGRAD = 4, OPT_ADADELTA = 5, OPT_NADAM = 6, OPT_FTRL = 7 };
+
+// One parameter, one step.  m / u are the parameter's two optimizer slots:
+//   Adamax, Adam, Nadam: first / second moment      SGD: momentum accumulator (m)        RMSprop: momentum (m), rms (u)
+//   Adagrad: accumulator (u, starts at initial_accumulator_value)                         Adadelta: accum (m), accum_update (u)
+//   Ftrl: accumulator (m, starts at initial_accumulator_value), linear (u)
 template <bool SPARSE>
-__device__ __forceinline__ float opt_step(int optimizer, float theta, float g, float& m, float& u, float lr_t,
-                                          float beta1, float beta2, float eps) {
-  if (optimizer == 0) {  // Adamax
-    m = SPARSE ? (m * beta1 + g * (1.f - beta1)) : (m + (g - m) * (1.f - beta1));
-    u = fmaxf(u * beta2, fabsf(g));
-    return theta - lr_t * (m / (u + eps));
-  } else if (optimizer == 1) {  // Adam
-    m = SPARSE ? (m * beta1 + g * (1.f - beta1)) : (m + (g - m) * (1.f - beta1));
-    u = SPARSE ? (u * beta2 + (g * g) * (1.f - beta2)) : (u + (g * g - u) * (1.f - beta2));
-    return theta - (m * lr_t) / (sqrtf(u) + eps);
+__device__ __forceinline__ float opt_step(const FitConsts& k, const FitState* st, float theta, float g, float& m, float& u,
+                                          float lr_t) {
+  switch (k.optimizer) {
+    case OPT_ADAMAX:
+      m = SPARSE ? (m * k.beta1 + g * (1.f - k.beta1)) : (m + (g - m) * (1.f - k.beta1));
+      u = fmaxf(u * k.beta2, fabsf(g));
+      return theta - lr_t * (m / (u + k.eps));
+    case OPT_ADAM:
+      m = SPARSE ? (m * k.beta1 + g * (1.f - k.beta1)) : (m + (g - m) * (1.f - k.beta1));
+      u = SPARSE ? (u * k.beta2 + (g * g) * (1.f - k.beta2)) : (u + (g * g - u) * (1.f - k.beta2));
+      return theta - (m * lr_t) / (sqrtf(u) + k.eps);
+    case OPT_SGD:  // ApplyGradientDescent / ApplyKerasMomentum
+      if (k.momentum == 0.f) return theta - lr_t * g;
+      m = m * k.momentum - lr_t * g;
+      return k.nesterov ? theta + m * k.momentum - lr_t * g : theta + m;
+    case OPT_RMSPROP:  // centered = False
+      u = k.rho * u + (1.f - k.rho) * (g * g);
+      if (k.momentum > 0.f) {  // fused ApplyRMSProp: epsilon inside the square root
+        m = k.momentum * m + lr_t * g * rsqrtf(u + k.eps);
+        return theta - m;
+      }
+      return theta - lr_t * g / (sqrtf(u) + k.eps);
+    case OPT_ADAGRAD:  // ApplyAdagradV2
+      u = u + g * g;
+      return theta - lr_t * g / (sqrtf(u) + k.eps);
+    case OPT_ADADELTA: {  // ApplyAdadelta
+      m = m * k.rho + (g * g) * (1.f - k.rho);
+      const float upd = sqrtf(u + k.eps) * rsqrtf(m + k.eps) * g;
+      u = u * k.rho + (upd * upd) * (1.f - k.rho);
+      return theta - upd * lr_t;
+    }
+    case OPT_NADAM: {  // Keras Nadam: aux = {1 - m_schedule_new, 1 - m_schedule_next, 1 - u_t, u_{t+1}}, aux2[0] = 1 - beta_2^t
+      const float g_prime = g / st->aux[0];
+      m = k.beta1 * m + (1.f - k.beta1) * g;
+      const float m_prime = m / st->aux[1];
+      u = k.beta2 * u + (1.f - k.beta2) * (g * g);
+      const float v_prime = u / st->aux2[0];
+      const float m_bar = st->aux[2] * g_prime + st->aux[3] * m_prime;
+      return theta - lr_t * m_bar / (sqrtf(v_prime) + k.eps);
+    }
+    default: {  // OPT_FTRL, ApplyFtrlV2 without shrinkage
+      const float acc_new = m + g * g;
+      const bool half = k.lr_power == -0.5f;
+      const float p_new = half ? sqrtf(acc_new) : powf(acc_new, -k.lr_power);
+      const float p_old = half ? sqrtf(m) : powf(m, -k.lr_power);
+      u += g - (p_new - p_old) / lr_t * theta;
+      const float quadratic = p_new / lr_t + 2.f * k.l2;
+      m = acc_new;
+      const float sgn = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+      return fabsf(u) > k.l1 ? (sgn * k.l1 - u) / quadratic : 0.f;
+    }
   }
-  return theta - lr_t * g;  // SGD without momentum
 }
 
 // Keras local_step = iterations + 1; powers evaluated in double and rounded once (identical in every kernel)
 __device__ __forceinline__ float bias_corrected_lr(const FitConsts& k, int step) {
   const double tt = (double)(step + 1);
-  const float b1p = (float)pow((double)k.beta1, tt);
-  if (k.optimizer == 0) return k.lr / (1.f - b1p);
-  if (k.optimizer == 1) {
+  if (k.optimizer == OPT_ADAMAX) return k.lr / (1.f - (float)pow((double)k.beta1, tt));
+  if (k.optimizer == OPT_ADAM) {
+    const float b1p = (float)pow((double)k.beta1, tt);
     const float b2p = (float)pow((double)k.beta2, tt);
     return k.lr * sqrtf(1.f - b2p) / (1.f - b1p);
   }
@@ -646,8 +697,8 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
       if (ci >= 0) {
         const float2 g = *reinterpret_cast<const float2*>(rowdc + r * 2);
         float mr = p.cm_r[ci], ur = p.cu_r[ci], mi = p.cm_i[ci], ui = p.cu_i[ci];
-        const float nr = opt_step<false>(p.k.optimizer, p.c_r_rw[ci], g.x, mr, ur, lr_fused, p.k.beta1, p.k.beta2, p.k.eps);
-        const float ni = opt_step<false>(p.k.optimizer, p.c_i_rw[ci], g.y, mi, ui, lr_fused, p.k.beta1, p.k.beta2, p.k.eps);
+        const float nr = opt_step<false>(p.k, st, p.c_r_rw[ci], g.x, mr, ur, lr_fused);
+        const float ni = opt_step<false>(p.k, st, p.c_i_rw[ci], g.y, mi, ui, lr_fused);
         p.cm_r[ci] = mr;
         p.cu_r[ci] = ur;
         p.cm_i[ci] = mi;
@@ -766,6 +817,19 @@ __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams 
 
   const int t = st->step;
   st->lr_t = bias_corrected_lr(p.k, t);
+  if (p.k.optimizer == OPT_NADAM) {  // Keras Nadam._prepare_local: momentum schedule with decay 0.004
+    const double ls = (double)(t + 1);
+    const float u_t = p.k.beta1 * (1.f - 0.5f * (float)pow(0.96, 0.004 * ls));
+    const float u_t1 = p.k.beta1 * (1.f - 0.5f * (float)pow(0.96, 0.004 * (ls + 1.0)));
+    const float ms_new = (float)(t == 0 ? 1.0 : st->m_schedule) * u_t;
+    const float ms_next = ms_new * u_t1;
+    st->m_schedule = (double)ms_new;
+    st->aux[0] = 1.f - ms_new;
+    st->aux[1] = 1.f - ms_next;
+    st->aux[2] = 1.f - u_t;
+    st->aux[3] = u_t1;
+    st->aux2[0] = 1.f - (float)pow((double)p.k.beta2, ls);
+  }
   int snap = 0;
   const int rec = t - p.k.n_skip;
   if (rec >= 0) {
@@ -953,8 +1017,8 @@ __global__ void __launch_bounds__(GK_THREADS) gains_kernel(const GainsParams p) 
   for (int c = 0; c < 2; ++c) {
     const size_t oc = o + c;
     float mr = p.m_r[oc], ur = p.u_r[oc], mi = p.m_i[oc], ui = p.u_i[oc];
-    const float nr = opt_step<true>(p.k.optimizer, gr[oc], a_r[c], mr, ur, lr_t, p.k.beta1, p.k.beta2, p.k.eps);
-    const float ni = opt_step<true>(p.k.optimizer, gi[oc], a_i[c], mi, ui, lr_t, p.k.beta1, p.k.beta2, p.k.eps);
+    const float nr = opt_step<true>(p.k, st, gr[oc], a_r[c], mr, ur, lr_t);
+    const float ni = opt_step<true>(p.k, st, gi[oc], a_i[c], mi, ui, lr_t);
     p.m_r[oc] = mr;
     p.u_r[oc] = ur;
     p.m_i[oc] = mi;
@@ -1122,8 +1186,8 @@ __global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
   }
   if (p.mode == 1) return;
   float mr = p.m_r[c], ur = p.u_r[c], mi = p.m_i[c], ui = p.u_i[c];
-  const float nr = opt_step<false>(p.k.optimizer, p.c_r[c], gr, mr, ur, st->lr_t, p.k.beta1, p.k.beta2, p.k.eps);
-  const float ni = opt_step<false>(p.k.optimizer, p.c_i[c], gi, mi, ui, st->lr_t, p.k.beta1, p.k.beta2, p.k.eps);
+  const float nr = opt_step<false>(p.k, st, p.c_r[c], gr, mr, ur, st->lr_t);
+  const float ni = opt_step<false>(p.k, st, p.c_i[c], gi, mi, ui, st->lr_t);
   p.m_r[c] = mr;
   p.u_r[c] = ur;
   p.m_i[c] = mi;
@@ -1210,6 +1274,9 @@ __global__ void snr_weight_kernel(float* __restrict__ w, const float2* __restric
     const float nw = (v.x * v.x + v.y * v.y) * w[b * nfp + f];
     w[b * nfp + f] = nw * scale;
   }
+}
+__global__ void fill_kernel(float* __restrict__ x, size_t n, float value) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = value;
 }
 __global__ void scale_kernel(float* __restrict__ x, size_t n, float scale) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

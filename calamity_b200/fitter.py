@@ -5,12 +5,18 @@ import numpy as np
 
 from . import _native as nat
 
-OPTIMIZER_IDS = {"Adamax": 0, "Adam": 1, "SGD": 2}
+OPTIMIZER_IDS = {"Adamax": 0, "Adam": 1, "SGD": 2, "RMSprop": 3, "Adagrad": 4, "Adadelta": 5, "Nadam": 6, "Ftrl": 7}
 # tf.keras.optimizers defaults (TensorFlow >= 2.4 OptimizerV2), used when **opt_kwargs omits a field
 KERAS_DEFAULTS = {
     "Adamax": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
     "Adam": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
-    "SGD": dict(learning_rate=0.01),
+    "SGD": dict(learning_rate=0.01, momentum=0.0, nesterov=False),
+    "RMSprop": dict(learning_rate=0.001, rho=0.9, momentum=0.0, epsilon=1e-7),
+    "Adagrad": dict(learning_rate=0.001, initial_accumulator_value=0.1, epsilon=1e-7),
+    "Adadelta": dict(learning_rate=0.001, rho=0.95, epsilon=1e-7),
+    "Nadam": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
+    "Ftrl": dict(learning_rate=0.001, learning_rate_power=-0.5, initial_accumulator_value=0.1,
+                 l1_regularization_strength=0.0, l2_regularization_strength=0.0),
 }
 # names the reference's OPTIMIZERS dict accepts (calibration.py:17-27); those without a device
 # implementation raise NotImplementedError instead of silently substituting something else
@@ -111,6 +117,11 @@ class FitPlan:
             regularization=1 if model_regularization == "sum" else 0, prior_r_sum=float(prior_r_sum),
             prior_i_sum=float(prior_i_sum), n_profile_steps=int(n_profile_steps), steps_per_sync=int(steps_per_sync),
             use_graph=int(bool(use_graph)), fuse_tail_update=int(bool(fuse_tail_update)),
+            rho=hp.get("rho", 0.0), momentum=hp.get("momentum", 0.0),
+            initial_accumulator_value=hp.get("initial_accumulator_value", 0.0),
+            l1_regularization_strength=hp.get("l1_regularization_strength", 0.0),
+            l2_regularization_strength=hp.get("l2_regularization_strength", 0.0),
+            learning_rate_power=hp.get("learning_rate_power", 0.0), nesterov=int(bool(hp.get("nesterov", False))),
         )
         hist = np.zeros(max(1, int(maxsteps)), dtype=np.float32)
         res = nat.FitResult()

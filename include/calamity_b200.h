@@ -42,8 +42,11 @@ enum {
   CALB2_ERR_NONFINITE = -6
 };
 
-/* tf.optimizers.* of calibration.py:17-27 that have a device implementation. */
-enum { CALB2_OPT_ADAMAX = 0, CALB2_OPT_ADAM = 1, CALB2_OPT_SGD = 2 };
+/* tf.optimizers.* of calibration.py:17-27 that have a device implementation (all but tensorflow-addons' LAMB). */
+enum {
+  CALB2_OPT_ADAMAX = 0, CALB2_OPT_ADAM = 1, CALB2_OPT_SGD = 2, CALB2_OPT_RMSPROP = 3, CALB2_OPT_ADAGRAD = 4,
+  CALB2_OPT_ADADELTA = 5, CALB2_OPT_NADAM = 6, CALB2_OPT_FTRL = 7
+};
 
 /* model_regularization of calibration.py:619-661: anything but "sum" is the plain chi-squared. */
 enum { CALB2_REG_NONE = 0, CALB2_REG_SUM = 1 };
@@ -82,6 +85,15 @@ typedef struct {
   int32_t use_graph;         /* 1 = replay a captured CUDA graph of steps_per_sync iterations */
   int32_t fuse_tail_update;  /* 1 = coefficient optimizer step inside the fused kernel's tail (only when every group is
                                 single-slot and regularization is NONE); measured slower than the split step, default 0 */
+  /* further Keras hyper-parameters (same names as the tf.keras.optimizers constructors); ignored by optimizers
+   * that do not have them */
+  float rho;                         /* RMSprop, Adadelta */
+  float momentum;                    /* SGD, RMSprop */
+  float initial_accumulator_value;   /* Adagrad, Ftrl */
+  float l1_regularization_strength;  /* Ftrl */
+  float l2_regularization_strength;  /* Ftrl */
+  float learning_rate_power;         /* Ftrl */
+  int32_t nesterov;                  /* SGD */
 } calb2_fit_options;
 
 typedef struct {

@@ -247,7 +247,13 @@ def loss_and_grads(g_r, g_i, fg_r, fg_i, data_r, data_i, wgts, fg_comps, corr_in
 KERAS_DEFAULTS = {
     "Adamax": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
     "Adam": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
-    "SGD": dict(learning_rate=0.01, momentum=0.0),
+    "SGD": dict(learning_rate=0.01, momentum=0.0, nesterov=False),
+    "RMSprop": dict(learning_rate=0.001, rho=0.9, momentum=0.0, epsilon=1e-7),
+    "Adagrad": dict(learning_rate=0.001, initial_accumulator_value=0.1, epsilon=1e-7),
+    "Adadelta": dict(learning_rate=0.001, rho=0.95, epsilon=1e-7),
+    "Nadam": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
+    "Ftrl": dict(learning_rate=0.001, learning_rate_power=-0.5, initial_accumulator_value=0.1,
+                 l1_regularization_strength=0.0, l2_regularization_strength=0.0),
 }
 
 
@@ -269,17 +275,84 @@ class KerasOptimizer:
         self.hp = dict(KERAS_DEFAULTS[name], **kwargs)
         self.iterations = 0
         self.slots = {}
+        self.m_schedule = 1.0  # Nadam `_m_cache`
+
+    def _other_rules(self, p, g, m, u, t, dt, nadam):
+        """RMSprop / Adagrad / Adadelta / Nadam / Ftrl (tf.keras.optimizers, OptimizerV2; the raw-op formulas
+        ApplyRMSProp, ApplyAdagradV2, ApplyAdadelta, ApplyFtrlV2 and Nadam._resource_apply_dense).  For these the
+        IndexedSlices (`*_sparse`) variants compute the same expressions, so there is one form."""
+        hp = self.hp
+        lr = dt(hp["learning_rate"])
+        one = dt(1)
+        if self.name == "RMSprop":
+            rho, mom, eps = dt(hp["rho"]), dt(hp["momentum"]), dt(hp["epsilon"])
+            u[...] = rho * u + (one - rho) * (g * g)
+            if mom > 0:  # fused op: epsilon inside the square root
+                m[...] = mom * m + lr * g / np.sqrt(u + eps)
+                p -= m
+            else:
+                p -= lr * g / (np.sqrt(u) + eps)
+        elif self.name == "Adagrad":
+            u += g * g
+            p -= lr * g / (np.sqrt(u) + dt(hp["epsilon"]))
+        elif self.name == "Adadelta":
+            rho, eps = dt(hp["rho"]), dt(hp["epsilon"])
+            m[...] = m * rho + (g * g) * (one - rho)
+            upd = np.sqrt(u + eps) / np.sqrt(m + eps) * g
+            u[...] = u * rho + (upd * upd) * (one - rho)
+            p -= upd * lr
+        elif self.name == "Nadam":
+            b1, b2, eps = dt(hp["beta_1"]), dt(hp["beta_2"]), dt(hp["epsilon"])
+            u_t, u_t1, ms_new, ms_next = nadam
+            g_prime = g / (one - ms_new)
+            m[...] = b1 * m + (one - b1) * g
+            m_prime = m / (one - ms_next)
+            u[...] = b2 * u + (one - b2) * (g * g)
+            v_prime = u / (one - dt(np.power(b2, dt(t))))
+            m_bar = (one - u_t) * g_prime + u_t1 * m_prime
+            p -= lr * m_bar / (np.sqrt(v_prime) + eps)
+        elif self.name == "Ftrl":
+            lp, l1, l2 = dt(hp["learning_rate_power"]), dt(hp["l1_regularization_strength"]), dt(hp["l2_regularization_strength"])
+            acc_new = m + g * g
+            pw = (lambda x: np.sqrt(x)) if lp == dt(-0.5) else (lambda x: np.power(x, -lp))
+            u += g - (pw(acc_new) - pw(m)) / lr * p
+            quadratic = pw(acc_new) / lr + dt(2) * l2
+            m[...] = acc_new
+            p[...] = np.where(np.abs(u) > l1, (np.sign(u) * l1 - u) / quadratic, dt(0))
+        else:
+            raise KeyError(self.name)
 
     def apply(self, params, grads, sparse_flags):
         self.iterations += 1
         t = self.iterations
+        nadam = None
+        if self.name == "Nadam":  # Nadam._prepare_local: one schedule update per step, shared by all variables
+            dt0 = params[0].dtype.type
+            b1 = dt0(self.hp["beta_1"])
+            u_t = b1 * (dt0(1) - dt0(0.5) * dt0(np.power(0.96, 0.004 * t)))
+            u_t1 = b1 * (dt0(1) - dt0(0.5) * dt0(np.power(0.96, 0.004 * (t + 1))))
+            ms_new = dt0(self.m_schedule) * u_t
+            self.m_schedule = float(ms_new)
+            nadam = (u_t, u_t1, ms_new, ms_new * u_t1)
         for n, (p, g, sp) in enumerate(zip(params, grads, sparse_flags)):
             dt = p.dtype.type
             if n not in self.slots:
                 self.slots[n] = (np.zeros_like(p), np.zeros_like(p))
+                if self.name == "Adagrad":
+                    self.slots[n][1][...] = dt(self.hp["initial_accumulator_value"])
+                if self.name == "Ftrl":
+                    self.slots[n][0][...] = dt(self.hp["initial_accumulator_value"])
             m, u = self.slots[n]
             if self.name == "SGD":
-                p -= dt(self.hp["learning_rate"]) * g
+                lr0, mom = dt(self.hp["learning_rate"]), dt(self.hp["momentum"])
+                if mom == 0:
+                    p -= lr0 * g
+                else:  # ApplyKerasMomentum
+                    m[...] = m * mom - lr0 * g
+                    p += (m * mom - lr0 * g) if self.hp["nesterov"] else m
+                continue
+            if self.name not in ("Adamax", "Adam"):
+                self._other_rules(p, g, m, u, t, dt, nadam)
                 continue
             lr, b1, b2, eps = (dt(self.hp[k]) for k in ("learning_rate", "beta_1", "beta_2", "epsilon"))
             b1p = dt(np.power(b1, dt(t)))

@@ -67,3 +67,75 @@ def test_numpy_and_torch_fit_loops_agree(optimizer):
               t["corr_inds"], dtype=torch.float64, **kw)
     assert np.allclose(a[4]["loss"], b[4]["loss"], rtol=1e-9, atol=0)
     assert rel_err(a[0], b[0]) < 1e-9 and rel_err(a[2][0], b[2][0]) < 1e-9
+
+
+def test_keras_rules_against_torch_optim_where_the_algebra_coincides():
+    """Independent check of the restated Keras update rules: torch.optim implements the same published algorithms for
+    SGD(+momentum/nesterov), RMSprop(momentum=0), Adagrad and Adadelta (up to the documented differences in where
+    epsilon sits, which are matched here by construction), so a few steps on random float64 data must agree."""
+    import torch
+
+    from oracle.restatement import KerasOptimizer
+
+    rng = np.random.default_rng(3)
+    x0 = rng.standard_normal(50)
+    grads = [rng.standard_normal(50) for _ in range(6)]
+
+    def run_keras(name, **kw):
+        p = x0.copy()
+        opt = KerasOptimizer(name, **kw)
+        for g in grads:
+            opt.apply([p], [g.copy()], [False])
+        return p
+
+    def run_torch(make):
+        p = torch.tensor(x0.copy(), requires_grad=True)
+        opt = make([p])
+        for g in grads:
+            p.grad = torch.tensor(g.copy())
+            opt.step()
+        return p.detach().numpy()
+
+    # Keras momentum accumulates -lr*g (velocity in parameter units); torch accumulates g and scales by lr: identical
+    # for a constant learning rate
+    np.testing.assert_allclose(run_keras("SGD", learning_rate=0.1, momentum=0.9),
+                               run_torch(lambda ps: torch.optim.SGD(ps, lr=0.1, momentum=0.9)), rtol=1e-12)
+    np.testing.assert_allclose(run_keras("SGD", learning_rate=0.1, momentum=0.9, nesterov=True),
+                               run_torch(lambda ps: torch.optim.SGD(ps, lr=0.1, momentum=0.9, nesterov=True)), rtol=1e-12)
+    np.testing.assert_allclose(run_keras("RMSprop", learning_rate=0.01, rho=0.9, epsilon=1e-7),
+                               run_torch(lambda ps: torch.optim.RMSprop(ps, lr=0.01, alpha=0.9, eps=1e-7)), rtol=1e-12)
+    np.testing.assert_allclose(run_keras("Adagrad", learning_rate=0.1, initial_accumulator_value=0.1, epsilon=1e-7),
+                               run_torch(lambda ps: torch.optim.Adagrad(ps, lr=0.1, initial_accumulator_value=0.1, eps=1e-7)),
+                               rtol=1e-12)
+    np.testing.assert_allclose(run_keras("Adadelta", learning_rate=1.0, rho=0.95, epsilon=1e-7),
+                               run_torch(lambda ps: torch.optim.Adadelta(ps, lr=1.0, rho=0.95, eps=1e-7)), rtol=1e-12)
+
+
+def test_keras_nadam_and_ftrl_closed_forms():
+    """Nadam's first step and Ftrl with l1 = l2 = 0 have closed forms that pin the restated rules."""
+    from oracle.restatement import KerasOptimizer
+
+    g = np.array([0.3, -2.0, 1e-3])
+    p = np.array([1.0, -1.0, 0.5])
+    opt = KerasOptimizer("Nadam", learning_rate=0.01)
+    q = p.copy()
+    opt.apply([q], [g.copy()], [False])
+    b1, b2, eps = 0.9, 0.999, 1e-7
+    u1 = b1 * (1 - 0.5 * 0.96 ** 0.004)
+    u2 = b1 * (1 - 0.5 * 0.96 ** 0.008)
+    m = (1 - b1) * g
+    v = (1 - b2) * g * g
+    mbar = (1 - u1) * g / (1 - u1) + u2 * (m / (1 - u1 * u2))
+    np.testing.assert_allclose(q, p - 0.01 * mbar / (np.sqrt(v / (1 - b2)) + eps), rtol=1e-12)
+    # Ftrl, no regularisation: theta_t = -lr * sum(z) / sqrt(acc) with the per-coordinate adaptive rate
+    opt = KerasOptimizer("Ftrl", learning_rate=0.1)
+    q = p.copy()
+    acc = np.full(3, 0.1)
+    lin = np.zeros(3)
+    for _ in range(3):
+        acc_new = acc + g * g
+        lin += g - (np.sqrt(acc_new) - np.sqrt(acc)) / 0.1 * q
+        expect = -lin / (np.sqrt(acc_new) / 0.1)
+        acc = acc_new
+        opt.apply([q], [g.copy()], [False])
+        np.testing.assert_allclose(q, expect, rtol=1e-12)
