@@ -203,8 +203,9 @@ def main():
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gain-gradient exchange fused into the update kernel over NVLink peer memory, or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-bls", type=int, default=384)
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    # CPU arm: ~10-20 s of host work -- 2048 of the 61 075 baselines (dense padded basis 1.7 GB), 20 steps
+    ap.add_argument("--cpu-sample-bls", type=int, default=2048)
+    ap.add_argument("--cpu-steps", type=int, default=20)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -1280,7 +1280,11 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
   CU(cudaMemcpyAsync(pl->state.p, &s0, sizeof(s0), cudaMemcpyHostToDevice, pl->stream));
 
   int chunk = o->steps_per_sync > 0 ? o->steps_per_sync : 32;
-  const bool time_heavy = !o->use_graph;
+  // use_graph: 1 = replay a captured graph, -1 = never, 0 = automatic: small problems are launch-latency bound (four
+  // launches of a few microseconds each per iteration), so they replay a graph of `chunk` iterations
+  const bool small_problem = (size_t)pl->a_floats * sizeof(float) < ((size_t)256 << 20);
+  const bool want_graph = pl->nranks == 1 && (o->use_graph > 0 || (o->use_graph == 0 && small_problem && total >= 64));
+  const bool time_heavy = !want_graph;
   std::vector<cudaEvent_t> evs;
   cudaEvent_t ev_begin, ev_end;
   CU(cudaEventCreate(&ev_begin));
@@ -1294,7 +1298,7 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
   long long launches = 0, heavy_launches = 0;
   double heavy_ms = 0.0;
   int rc = 0;
-  if (o->use_graph && pl->nranks == 1) {
+  if (want_graph) {
     long long dummy = 0;
     CU(cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < chunk && !rc; ++i) rc = enqueue_step(pl, k, sum, freeze, o->fuse_tail_update != 0, pl->hist.p, nullptr, nullptr, &dummy);

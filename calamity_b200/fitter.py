@@ -100,7 +100,7 @@ class FitPlan:
     # -- the loop
     def fit(self, optimizer="Adamax", maxsteps=10000, tol=1e-14, use_min=False, freeze_model=False,
             model_regularization=None, prior_r_sum=0.0, prior_i_sum=0.0, n_profile_steps=0, steps_per_sync=0,
-            use_graph=False, fuse_tail_update=False, **opt_kwargs):
+            use_graph=None, fuse_tail_update=False, **opt_kwargs):
         if optimizer not in REFERENCE_OPTIMIZERS:
             raise KeyError(optimizer)  # calibration.py:571: OPTIMIZERS[optimizer]
         if optimizer not in OPTIMIZER_IDS:
@@ -116,7 +116,7 @@ class FitPlan:
             use_min=int(bool(use_min)), freeze_model=int(bool(freeze_model)),
             regularization=1 if model_regularization == "sum" else 0, prior_r_sum=float(prior_r_sum),
             prior_i_sum=float(prior_i_sum), n_profile_steps=int(n_profile_steps), steps_per_sync=int(steps_per_sync),
-            use_graph=int(bool(use_graph)), fuse_tail_update=int(bool(fuse_tail_update)),
+            use_graph=0 if use_graph is None else (1 if use_graph else -1), fuse_tail_update=int(bool(fuse_tail_update)),
             rho=hp.get("rho", 0.0), momentum=hp.get("momentum", 0.0),
             initial_accumulator_value=hp.get("initial_accumulator_value", 0.0),
             l1_regularization_strength=hp.get("l1_regularization_strength", 0.0),

@@ -82,7 +82,8 @@ typedef struct {
   float prior_i_sum;
   int32_t n_profile_steps;   /* extra real steps before the warm-up step (calibration.py:681-687) */
   int32_t steps_per_sync;    /* 0 = default; iterations enqueued between host checks of the stop flag */
-  int32_t use_graph;         /* 1 = replay a captured CUDA graph of steps_per_sync iterations */
+  int32_t use_graph;         /* 1 = replay a captured CUDA graph of steps_per_sync iterations, -1 = never, 0 = automatic
+                                (graphs for small, launch-latency-bound problems on a single GPU) */
   int32_t fuse_tail_update;  /* 1 = coefficient optimizer step inside the fused kernel's tail (only when every group is
                                 single-slot and regularization is NONE); measured slower than the split step, default 0 */
   /* further Keras hyper-parameters (same names as the tf.keras.optimizers constructors); ignored by optimizers
