@@ -28,33 +28,34 @@ class PlanDesc(C.Structure):
         ("bl_ant0", C.POINTER(C.c_int32)),
         ("bl_ant1", C.POINTER(C.c_int32)),
         ("tile_freqs", C.c_int32),
+        ("dtype", C.c_int32),
     ]
 
 
 class FitOptions(C.Structure):
     _fields_ = [
         ("optimizer", C.c_int32),
-        ("learning_rate", C.c_float),
-        ("beta_1", C.c_float),
-        ("beta_2", C.c_float),
-        ("epsilon", C.c_float),
         ("maxsteps", C.c_int32),
+        ("learning_rate", C.c_double),
+        ("beta_1", C.c_double),
+        ("beta_2", C.c_double),
+        ("epsilon", C.c_double),
         ("tol", C.c_double),
         ("use_min", C.c_int32),
         ("freeze_model", C.c_int32),
         ("regularization", C.c_int32),
-        ("prior_r_sum", C.c_float),
-        ("prior_i_sum", C.c_float),
+        ("prior_r_sum", C.c_double),
+        ("prior_i_sum", C.c_double),
         ("n_profile_steps", C.c_int32),
         ("steps_per_sync", C.c_int32),
         ("use_graph", C.c_int32),
         ("fuse_tail_update", C.c_int32),
-        ("rho", C.c_float),
-        ("momentum", C.c_float),
-        ("initial_accumulator_value", C.c_float),
-        ("l1_regularization_strength", C.c_float),
-        ("l2_regularization_strength", C.c_float),
-        ("learning_rate_power", C.c_float),
+        ("rho", C.c_double),
+        ("momentum", C.c_double),
+        ("initial_accumulator_value", C.c_double),
+        ("l1_regularization_strength", C.c_double),
+        ("l2_regularization_strength", C.c_double),
+        ("learning_rate_power", C.c_double),
         ("nesterov", C.c_int32),
     ]
 
@@ -83,11 +84,14 @@ class PlanInfo(C.Structure):
         ("tile_freqs", C.c_int32),
         ("rows_per_item_max", C.c_int32),
         ("device_bytes", C.c_int64),
+        ("generic", C.c_int32),
+        ("dtype", C.c_int32),
     ]
 
 
 # every symbol include/calamity_b200.h declares, with its argument types
-_FP = C.POINTER(C.c_float)
+_FP = C.c_void_p  # float32 or float64 elements, per the plan's dtype
+_DP = C.POINTER(C.c_double)
 _SIGNATURES = {
     "calb2_last_error": (C.c_char_p, []),
     "calb2_version": (C.c_char_p, []),
@@ -99,10 +103,10 @@ _SIGNATURES = {
     "calb2_set_gains": (C.c_int, [C.c_void_p, _FP, _FP]),
     "calb2_set_coeffs": (C.c_int, [C.c_void_p, _FP, _FP]),
     "calb2_init_coeffs": (C.c_int, [C.c_void_p, _FP, _FP]),
-    "calb2_prior_sums": (C.c_int, [C.c_void_p, _FP, _FP, _FP, _FP]),
+    "calb2_prior_sums": (C.c_int, [C.c_void_p, _FP, _FP, _DP, _DP]),
     "calb2_apply_model_snr_weights": (C.c_int, [C.c_void_p]),
     "calb2_fit": (C.c_int, [C.c_void_p, C.POINTER(FitOptions), _FP, C.POINTER(FitResult)]),
-    "calb2_loss_and_grads": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, _FP, _FP, _FP, _FP, _FP]),
+    "calb2_loss_and_grads": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, _DP, _FP, _FP, _FP, _FP]),
     "calb2_get_gains": (C.c_int, [C.c_void_p, _FP, _FP]),
     "calb2_get_coeffs": (C.c_int, [C.c_void_p, _FP, _FP]),
     "calb2_get_model": (C.c_int, [C.c_void_p, _FP, _FP]),
@@ -144,10 +148,13 @@ def check(rc):
         raise NativeError(f"calamity_b200 native call failed ({rc}): {msg}")
 
 
-def fptr(arr):
-    """float32 C-contiguous ndarray -> float*; the caller keeps `arr` alive for the duration of the call."""
-    assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"], (arr.dtype, arr.flags)
-    return arr.ctypes.data_as(_FP)
+DTYPE_IDS = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}
+
+
+def fptr(arr, dtype=np.float32):
+    """C-contiguous ndarray of the plan's dtype -> void*; the caller keeps `arr` alive for the duration of the call."""
+    assert arr.dtype == np.dtype(dtype) and arr.flags["C_CONTIGUOUS"], (arr.dtype, dtype, arr.flags)
+    return arr.ctypes.data_as(C.c_void_p)
 
 
 def iptr(arr):

@@ -84,10 +84,19 @@ def chunk_fg_comp_dict_by_nbls(fg_model_comps_dict, use_redundancy=False, grp_si
     return {(nbl, width[nbl]): {grp: ordered[grp] for grp in grps} for nbl, grps in by_size.items()}
 
 
-def _layout_from_dict(fg_model_comps_dict, ants_map, nfreqs, use_redundancy, grp_size_threshold, nants=None):
+def _layout_from_dict(fg_model_comps_dict, ants_map, nfreqs, use_redundancy, grp_size_threshold, nants=None,
+                      dtype=np.float32):
     chunked = chunk_fg_comp_dict_by_nbls(fg_model_comps_dict, use_redundancy=use_redundancy,
                                          grp_size_threshold=grp_size_threshold)
-    return RaggedLayout.from_chunked_dict(chunked, ants_map, nfreqs, nants=nants)
+    return RaggedLayout.from_chunked_dict(chunked, ants_map, nfreqs, nants=nants, dtype=dtype)
+
+
+def _fit_dtype(dtype):
+    """np.float32 -> fused sm_100a kernels, np.float64 -> the generic device path (calibration.py:974, 1795)."""
+    dt = np.dtype(dtype)
+    if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise TypeError(f"dtype must be np.float32 or np.float64, not {dtype!r}")
+    return dt
 
 
 def tensorize_fg_model_comps_dict(
@@ -277,8 +286,7 @@ def _run_fit(plan, lay, g_r, g_i, fg_r, fg_i, use_min, tol, maxsteps, optimizer,
     and translate the results back to the reference's shapes."""
     if optimizer not in OPTIMIZERS:
         raise KeyError(optimizer)  # calibration.py:571
-    if np.dtype(dtype) != np.float32:
-        raise NotImplementedError("the device fit computes in float32 only (precision=64 is not available yet)")
+    dtype = _fit_dtype(dtype)
     echo(f"{datetime.datetime.now()} Performing gradient descent on {np.prod(np.shape(g_r))} complex gain parameters...",
          verbose=verbose)
     if not freeze_model:
@@ -298,7 +306,7 @@ def _run_fit(plan, lay, g_r, g_i, fg_r, fg_i, use_min, tol, maxsteps, optimizer,
         raise UnboundLocalError("local variable 'fg_r_opt' referenced before assignment")  # calibration.py:738
     out_gr, out_gi = plan.get_gains()
     c_r, c_i = plan.get_coeffs()
-    fit_history = {"loss": [np.float32(x) for x in hist]}
+    fit_history = {"loss": [dtype.type(x) for x in hist]}
     echo(f"{datetime.datetime.now()} Finished Gradient Descent. MSE of {res['final_loss']:.2e}...\n", verbose=verbose)
     return out_gr, out_gi, c_r, c_i, fit_history
 
@@ -344,7 +352,7 @@ def fit_gains_and_foregrounds(
     if optimizer not in OPTIMIZERS:
         raise KeyError(optimizer)
     nants = int(np.shape(g_r)[0])
-    lay = RaggedLayout.from_dense([np.asarray(c) for c in fg_comps], corr_inds, nants)
+    lay = RaggedLayout.from_dense([np.asarray(c) for c in fg_comps], corr_inds, nants, dtype=_fit_dtype(dtype))
     with FitPlan(lay, device=_device_index()) as plan:
         w_flat = lay.flatten_data(wgts)
         plan.set_integration(lay.flatten_data(data_r), lay.flatten_data(data_i), w_flat)
@@ -359,8 +367,8 @@ def fit_gains_and_foregrounds(
     if freeze_model:
         fg_r_opt, fg_i_opt = fg_r, fg_i  # calibration.py:730-732: handed back untouched
     else:
-        fg_r_opt = [_as_tensor(t) for t in lay.unflatten_coeffs(c_r, template=fg_r)]
-        fg_i_opt = [_as_tensor(t) for t in lay.unflatten_coeffs(c_i, template=fg_i)]
+        fg_r_opt = [_as_tensor(t) for t in lay.unflatten_coeffs(c_r, template=fg_r, dtype=lay.dtype)]
+        fg_i_opt = [_as_tensor(t) for t in lay.unflatten_coeffs(c_i, template=fg_i, dtype=lay.dtype)]
     return _as_tensor(out_gr), _as_tensor(out_gi), fg_r_opt, fg_i_opt, fit_history
 
 
@@ -423,8 +431,8 @@ def tensorize_fg_coeffs(
             if len(empty) > 0:
                 c[int(empty.min()) :, g] = 0.0
         trimmed.append(c)
-    lay = RaggedLayout.from_dense(trimmed, corr, nants)
     dtype = np.asarray(data[0]).dtype
+    lay = RaggedLayout.from_dense(trimmed, corr, nants, dtype=np.float64 if dtype == np.float64 else np.float32)
     with FitPlan(lay, device=_device_index()) as plan:
         flat = lay.flatten_data(data)
         plan.set_integration(flat, flat, lay.flatten_data(wgts))
@@ -493,7 +501,7 @@ def calibrate_and_model_tensor(
 ):
     """Simultaneous gain calibration and foreground modelling of every (polarization, time) in `uvdata` --
     calibration.py:963-1331.  Returns (model, resid, gains, fit_history) exactly as the reference does;
-    fit_history[polnum][time_index]['loss'] is a list of np.float32.
+    fit_history[polnum][time_index]['loss'] is a list of np.float32 (np.float64 when dtype=np.float64).
 
     The foreground basis is uploaded to the device once per call (the reference tensorises it once per call
     too, calibration.py:1143-1152); each integration then only moves its data, weights and gains.
@@ -521,8 +529,9 @@ def calibrate_and_model_tensor(
     fit_history = {}
     ants_map = {ant: i for i, ant in enumerate(gains.ant_array)}
     echo(f"{datetime.datetime.now()} Computing foreground components matrices...\n", verbose=verbose)
+    fdt = _fit_dtype(dtype)
     lay = _layout_from_dict(fg_model_comps_dict, ants_map, sky_model.Nfreqs, use_redundancy, grp_size_threshold,
-                            nants=max(len(ants_map), uvdata.Nants_data))
+                            nants=max(len(ants_map), uvdata.Nants_data), dtype=fdt)
     bl_pairs = list(zip(lay.bl_ant0.tolist(), lay.bl_ant1.tolist()))
     del fg_model_comps_dict
     plan = FitPlan(lay, device=_device_index())
@@ -541,17 +550,17 @@ def calibrate_and_model_tensor(
                     rmsdata = np.sqrt(np.mean(np.abs(uvdata.data_array[bltsel, 0, :, polnum][unflagged]) ** 2.0))
                     echo(f"{datetime.datetime.now()} Tensorizing data...\n", verbose=verbose)
                     d_r, d_i, w = _tensorize_data_flat(uvdata, bl_pairs, ants_map, pol, time, rmsdata, weights,
-                                                       nsamples_in_weights, np.float32)
+                                                       nsamples_in_weights, fdt)
                     plan.set_integration(d_r, d_i, w)
                     s_r = s_i = None
                     if sky_model is not None:
                         echo(f"{datetime.datetime.now()} Tensorizing sky model...\n", verbose=verbose)
                         s_r, s_i, _ = _tensorize_data_flat(sky_model, bl_pairs, ants_map, pol, time, rmsdata, weights,
-                                                           False, np.float32)
+                                                           False, fdt)
                     if first_time or not init_guesses_from_previous_time_step:
                         first_time = False
                         echo(f"{datetime.datetime.now()} Tensorizing Gains...\n", verbose=verbose)
-                        g_r, g_i = tensorize_gains(gains, dtype=np.float32, time=time, polarization=pol)
+                        g_r, g_i = tensorize_gains(gains, dtype=fdt, time=time, polarization=pol)
                         g_r, g_i = _pad_gain_rows(g_r, lay.nants), _pad_gain_rows(g_i, lay.nants, fill=0.0)
                         plan.set_gains(g_r, g_i)
                         echo(f"{datetime.datetime.now()} Tensorizing Foreground coeffs...\n", verbose=verbose)
@@ -600,12 +609,14 @@ def calibrate_and_model_tensor(
 
 
 def _pad_gain_rows(g, nants, fill=1.0):
-    g = np.asarray(g, dtype=np.float32)
+    g = np.asarray(g)
+    if g.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        g = g.astype(np.float32)
     if g.ndim == 1:
         g = g[None, :]
     if g.shape[0] >= nants:
         return g
-    pad = np.full((nants - g.shape[0], g.shape[1]), fill, dtype=np.float32)
+    pad = np.full((nants - g.shape[0], g.shape[1]), fill, dtype=g.dtype)
     return np.concatenate([g, pad], axis=0)
 
 

@@ -16,6 +16,7 @@
 #include "../../include/calamity_b200.h"
 #include "calfit_kernels.cuh"
 #include "calfit_setup.cuh"
+#include "calfit_generic.cuh"
 
 namespace calb2 {
 
@@ -100,8 +101,13 @@ static constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0;
 }  // namespace calb2
 
 using namespace calb2;
+namespace calb2 {
+struct GenericBase;
+}
 
 struct calb2_plan {
+  calb2::GenericBase* gen = nullptr;  // float64 plans and oversized groups: generic unfused device path
+  int dtype = 0;
   int device = 0, nants = 0, nf = 0, ngroups = 0;
   int FL = 0, G = 0, FT = 0, KMAX = 0, nfp = 0, ntiles = 0, RPT = RPT_DEFAULT, NW = 8;
   long long nbls = 0, nslots = 0, ncoef = 0, rows_total = 0, a_floats = 0, n_a_nz = 0;
@@ -669,6 +675,8 @@ static int init_coeffs_impl(calb2_plan* pl, const float* sky_r, const float* sky
 
 }  // namespace calb2
 
+#include "calfit_generic_host.cuh"
+
 // ====================================================================================================
 // C ABI
 // ====================================================================================================
@@ -682,10 +690,18 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   if (d->nants <= 0 || d->nfreqs <= 0 || d->ngroups <= 0) return fail(CALB2_ERR_ARG, "empty problem");
   const int rpt = RPT_DEFAULT, nwarp = 8;
   int fl = 0;
-  if (int r = choose_fl(d, rpt, nwarp, &fl)) return r;
+  if (d->dtype != CALB2_F32 && d->dtype != CALB2_F64) return fail(CALB2_ERR_ARG, "dtype must be CALB2_F32 or CALB2_F64");
+  // float64, or a group with more basis vectors than the fused kernel stages: the generic unfused path
+  bool generic = d->dtype == CALB2_F64 || (getenv("CALB2_GENERIC") && atoi(getenv("CALB2_GENERIC")) != 0);
+  if (int r = choose_fl(d, rpt, nwarp, &fl)) {
+    if (r != CALB2_ERR_UNSUPPORTED || d->tile_freqs) return r;
+    generic = true;
+    fl = 8;
+  }
   CU(cudaSetDevice(d->device));
   calb2_plan* pl = new calb2_plan();
   pl->device = d->device;
+  pl->dtype = d->dtype;
   pl->nants = d->nants;
   pl->nf = d->nfreqs;
   pl->ngroups = d->ngroups;
@@ -846,6 +862,37 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
 #define TRY(x)          \
   if (!rc) rc = (x);
   CU(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  if (generic) {
+    TRY(upload(pl->d_slot_bl0, pl->slot_bl0, pl));
+    TRY(upload(pl->d_bl_ant0, pl->bl_ant0, pl));
+    TRY(upload(pl->d_bl_ant1, pl->bl_ant1, pl));
+    TRY(upload(pl->d_bl_slot, pl->bl_slot, pl));
+    TRY(upload(pl->ant_ptr, ant_ptr, pl));
+    TRY(upload(pl->ant_ent, ant_ent, pl));
+    TRY(upload(pl->ant_partner, ant_partner, pl));
+    TRY(upload(pl->coef_grp, coef_grp, pl));
+    TRY(upload(pl->d_grp_nslots, pl->grp_nslots, pl));
+    TRY(upload(pl->d_grp_slot0, pl->grp_slot0, pl));
+    TRY(upload(pl->d_grp_coef0, pl->grp_coef0, pl));
+    TRY(upload(pl->d_grp_ncomp, pl->grp_ncomp, pl));
+    if (!rc) {
+      if (d->dtype == CALB2_F64) {
+        auto* g = new GenericPlan<double>();
+        pl->gen = g;
+        rc = g->init(pl);
+      } else {
+        auto* g = new GenericPlan<float>();
+        pl->gen = g;
+        rc = g->init(pl);
+      }
+    }
+    if (rc) {
+      calb2_plan_destroy(pl);
+      return rc;
+    }
+    *out = pl;
+    return 0;
+  }
   TRY(dalloc(pl->A, (size_t)pl->a_floats, pl));
   TRY(upload(pl->d_items, pl->items, pl));
   TRY(upload(pl->row_slot, row_slot, pl));
@@ -911,6 +958,8 @@ int calb2_plan_destroy(calb2_plan* pl) {
   if (!pl) return 0;
   cudaSetDevice(pl->device);
   if (pl->stream) cudaStreamSynchronize(pl->stream);
+  delete pl->gen;
+  pl->gen = nullptr;
   if (pl->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pl->comm);
   for (int r = 0; r < CALB2_MAX_RANKS; ++r)
     if (pl->xpeer[r]) cudaIpcCloseMemHandle(pl->xpeer[r]);
@@ -959,13 +1008,24 @@ int calb2_plan_get_info(const calb2_plan* pl, calb2_plan_info* info) {
   info->tile_freqs = pl->FT;
   info->rows_per_item_max = pl->KMAX;
   info->device_bytes = (int64_t)pl->device_bytes;
+  info->generic = pl->gen ? 1 : 0;
+  info->dtype = pl->dtype;
+  if (pl->gen) {
+    info->n_a_stored = pl->n_a_nz;
+    info->nitems = 0;
+    info->tile_freqs = 0;
+    info->rows_per_item_max = 0;
+    info->device_bytes += (int64_t)pl->gen->device_bytes();
+  }
   return 0;
 }
 
-int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const float* const* blocks) {
-  if (!pl || !blocks) return fail(CALB2_ERR_ARG, "null argument");
+int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* const* blocks_v) {
+  if (!pl || !blocks_v) return fail(CALB2_ERR_ARG, "null argument");
   if (g0 < 0 || ng < 0 || g0 + ng > pl->ngroups) return fail(CALB2_ERR_ARG, "group range out of bounds");
   CU(cudaSetDevice(pl->device));
+  if (pl->gen) return pl->gen->set_basis(g0, ng, blocks_v);
+  const float* const* blocks = reinterpret_cast<const float* const*>(blocks_v);
   std::vector<RetileJob> jobs;
   std::unordered_map<const float*, long long> seen;
   size_t used = 0;
@@ -1021,9 +1081,11 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const float* co
   return 0;
 }
 
-int calb2_set_integration(calb2_plan* pl, const float* data_r, const float* data_i, const float* wgts) {
-  if (!pl || !data_r || !data_i || !wgts) return fail(CALB2_ERR_ARG, "null argument");
+int calb2_set_integration(calb2_plan* pl, const void* data_r_v, const void* data_i_v, const void* wgts_v) {
+  if (!pl || !data_r_v || !data_i_v || !wgts_v) return fail(CALB2_ERR_ARG, "null argument");
   CU(cudaSetDevice(pl->device));
+  if (pl->gen) return pl->gen->set_integration(data_r_v, data_i_v, wgts_v);
+  const float *data_r = (const float*)data_r_v, *data_i = (const float*)data_i_v, *wgts = (const float*)wgts_v;
   if (int r = upload_padded(pl, data_r, pl->d_r.p, (size_t)pl->nbls, 0.f)) return r;
   if (int r = upload_padded(pl, data_i, pl->d_i.p, (size_t)pl->nbls, 0.f)) return r;
   if (int r = upload_padded(pl, wgts, pl->w.p, (size_t)pl->nbls, 0.f)) return r;
@@ -1031,9 +1093,11 @@ int calb2_set_integration(calb2_plan* pl, const float* data_r, const float* data
   return 0;
 }
 
-int calb2_set_gains(calb2_plan* pl, const float* g_r, const float* g_i) {
-  if (!pl || !g_r || !g_i) return fail(CALB2_ERR_ARG, "null argument");
+int calb2_set_gains(calb2_plan* pl, const void* g_r_v, const void* g_i_v) {
+  if (!pl || !g_r_v || !g_i_v) return fail(CALB2_ERR_ARG, "null argument");
   CU(cudaSetDevice(pl->device));
+  if (pl->gen) return pl->gen->set_gains(g_r_v, g_i_v);
+  const float *g_r = (const float*)g_r_v, *g_i = (const float*)g_i_v;
   pl->cur_buf = 0;
   if (int r = upload_padded(pl, g_r, pl->g_r[0].p, (size_t)pl->nants, 1.f)) return r;
   if (int r = upload_padded(pl, g_i, pl->g_i[0].p, (size_t)pl->nants, 0.f)) return r;
@@ -1041,35 +1105,40 @@ int calb2_set_gains(calb2_plan* pl, const float* g_r, const float* g_i) {
   return 0;
 }
 
-int calb2_set_coeffs(calb2_plan* pl, const float* coef_r, const float* coef_i) {
+int calb2_set_coeffs(calb2_plan* pl, const void* coef_r, const void* coef_i) {
   if (!pl || !coef_r || !coef_i) return fail(CALB2_ERR_ARG, "null argument");
   CU(cudaSetDevice(pl->device));
+  if (pl->gen) return pl->gen->set_coeffs(coef_r, coef_i);
   CU(cudaMemcpy(pl->c_r.p, coef_r, pl->ncoef * sizeof(float), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(pl->c_i.p, coef_i, pl->ncoef * sizeof(float), cudaMemcpyHostToDevice));
   pl->have_coeffs = true;
   return 0;
 }
 
-int calb2_get_gains(calb2_plan* pl, float* g_r, float* g_i) {
-  if (!pl || !g_r || !g_i) return fail(CALB2_ERR_ARG, "null argument");
+int calb2_get_gains(calb2_plan* pl, void* g_r_v, void* g_i_v) {
+  if (!pl || !g_r_v || !g_i_v) return fail(CALB2_ERR_ARG, "null argument");
   CU(cudaSetDevice(pl->device));
+  if (pl->gen) return pl->gen->get_gains(g_r_v, g_i_v);
+  float *g_r = (float*)g_r_v, *g_i = (float*)g_i_v;
   if (int r = download_unpadded(pl, pl->g_r[pl->cur_buf].p, g_r, (size_t)pl->nants)) return r;
   return download_unpadded(pl, pl->g_i[pl->cur_buf].p, g_i, (size_t)pl->nants);
 }
 
-int calb2_get_coeffs(calb2_plan* pl, float* coef_r, float* coef_i) {
+int calb2_get_coeffs(calb2_plan* pl, void* coef_r, void* coef_i) {
   if (!pl || !coef_r || !coef_i) return fail(CALB2_ERR_ARG, "null argument");
   CU(cudaSetDevice(pl->device));
+  if (pl->gen) return pl->gen->get_coeffs(coef_r, coef_i);
   CU(cudaStreamSynchronize(pl->stream));
   CU(cudaMemcpy(coef_r, pl->c_r.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(coef_i, pl->c_i.p, pl->ncoef * sizeof(float), cudaMemcpyDeviceToHost));
   return 0;
 }
 
-int calb2_get_weights(calb2_plan* pl, float* wgts) {
+int calb2_get_weights(calb2_plan* pl, void* wgts) {
   if (!pl || !wgts) return fail(CALB2_ERR_ARG, "null argument");
   CU(cudaSetDevice(pl->device));
-  return download_unpadded(pl, pl->w.p, wgts, (size_t)pl->nbls);
+  if (pl->gen) return pl->gen->get_weights(wgts);
+  return download_unpadded(pl, pl->w.p, (float*)wgts, (size_t)pl->nbls);
 }
 
 static int run_forward_store_v(calb2_plan* pl) {
@@ -1080,8 +1149,13 @@ static int run_forward_store_v(calb2_plan* pl) {
   return 0;
 }
 
-int calb2_get_model(calb2_plan* pl, float* model_r, float* model_i) {
-  if (!pl || !model_r || !model_i) return fail(CALB2_ERR_ARG, "null argument");
+int calb2_get_model(calb2_plan* pl, void* model_r_v, void* model_i_v) {
+  if (!pl || !model_r_v || !model_i_v) return fail(CALB2_ERR_ARG, "null argument");
+  if (pl->gen) {
+    CU(cudaSetDevice(pl->device));
+    return pl->gen->get_model(model_r_v, model_i_v);
+  }
+  float *model_r = (float*)model_r_v, *model_i = (float*)model_i_v;
   if (!pl->have_data || !pl->have_gains || !pl->have_coeffs) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
   CU(cudaSetDevice(pl->device));
   if (int r = run_forward_store_v(pl)) return r;
@@ -1114,8 +1188,13 @@ static int device_sum(calb2_plan* pl, const float* x, const float* y, size_t n, 
   return 0;
 }
 
-int calb2_prior_sums(calb2_plan* pl, const float* sky_r, const float* sky_i, float* prior_r, float* prior_i) {
-  if (!pl || !sky_r || !sky_i || !prior_r || !prior_i) return fail(CALB2_ERR_ARG, "null argument");
+int calb2_prior_sums(calb2_plan* pl, const void* sky_r_v, const void* sky_i_v, double* prior_r, double* prior_i) {
+  if (!pl || !sky_r_v || !sky_i_v || !prior_r || !prior_i) return fail(CALB2_ERR_ARG, "null argument");
+  if (pl->gen) {
+    CU(cudaSetDevice(pl->device));
+    return pl->gen->prior_sums(sky_r_v, sky_i_v, prior_r, prior_i);
+  }
+  const float *sky_r = (const float*)sky_r_v, *sky_i = (const float*)sky_i_v;
   if (!pl->have_data) return fail(CALB2_ERR_STATE, "set_integration first (weights)");
   CU(cudaSetDevice(pl->device));
   const size_t nd = (size_t)pl->nbls * pl->nfp;
@@ -1124,17 +1203,18 @@ int calb2_prior_sums(calb2_plan* pl, const float* sky_r, const float* sky_i, flo
   double t = 0.0;
   if (int r = upload_padded(pl, sky_r, pl->scratch_f.p, (size_t)pl->nbls, 0.f)) return r;
   if (int r = device_sum(pl, pl->scratch_f.p, pl->w.p, nd, &t)) return r;
-  *prior_r = (float)t;
+  *prior_r = (double)(float)t;
   if (int r = upload_padded(pl, sky_i, pl->scratch_f.p, (size_t)pl->nbls, 0.f)) return r;
   if (int r = device_sum(pl, pl->scratch_f.p, pl->w.p, nd, &t)) return r;
-  *prior_i = (float)t;
+  *prior_i = (double)(float)t;
   return 0;
 }
 
 int calb2_apply_model_snr_weights(calb2_plan* pl) {
   if (!pl) return fail(CALB2_ERR_ARG, "null argument");
-  if (!pl->have_data || !pl->have_coeffs || !pl->have_gains) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
   CU(cudaSetDevice(pl->device));
+  if (pl->gen) return pl->gen->apply_snr_weights();
+  if (!pl->have_data || !pl->have_coeffs || !pl->have_gains) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
   if (int r = run_forward_store_v(pl)) return r;
   snr_weight_kernel<<<(unsigned)pl->nbls, 128, 0, pl->stream>>>(pl->w.p, pl->vout.p, pl->d_bl_slot.p, pl->nfp, 1.f);
   CU(cudaGetLastError());
@@ -1147,16 +1227,22 @@ int calb2_apply_model_snr_weights(calb2_plan* pl) {
   return 0;
 }
 
-int calb2_init_coeffs(calb2_plan* pl, const float* sky_r, const float* sky_i) {
+int calb2_init_coeffs(calb2_plan* pl, const void* sky_r, const void* sky_i) {
   if (!pl || !sky_r || !sky_i) return fail(CALB2_ERR_ARG, "null argument");
-  if (!pl->have_data) return fail(CALB2_ERR_STATE, "set_integration first (weights)");
   CU(cudaSetDevice(pl->device));
-  return init_coeffs_impl(pl, sky_r, sky_i);
+  if (pl->gen) return pl->gen->init_coeffs(sky_r, sky_i);
+  if (!pl->have_data) return fail(CALB2_ERR_STATE, "set_integration first (weights)");
+  return init_coeffs_impl(pl, (const float*)sky_r, (const float*)sky_i);
 }
 
-int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, float prior_i, float* loss, float* dg_r,
-                         float* dg_i, float* dc_r, float* dc_i) {
+int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, double prior_r, double prior_i, double* loss, void* dg_r_v,
+                         void* dg_i_v, void* dc_r_v, void* dc_i_v) {
   if (!pl) return fail(CALB2_ERR_ARG, "null argument");
+  if (pl->gen) {
+    CU(cudaSetDevice(pl->device));
+    return pl->gen->loss_and_grads(regularization, prior_r, prior_i, loss, dg_r_v, dg_i_v, dc_r_v, dc_i_v);
+  }
+  float *dg_r = (float*)dg_r_v, *dg_i = (float*)dg_i_v, *dc_r = (float*)dc_r_v, *dc_i = (float*)dc_i_v;
   if (!pl->have_data || !pl->have_gains || !pl->have_coeffs) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
   CU(cudaSetDevice(pl->device));
   const bool sum = regularization == CALB2_REG_SUM;
@@ -1166,8 +1252,8 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, 
   if (int r = set_eval_state(pl)) return r;
   FitConsts k{};
   k.regularization = regularization;
-  k.prior_r = prior_r;
-  k.prior_i = prior_i;
+  k.prior_r = (float)prior_r;
+  k.prior_i = (float)prior_i;
   HeavyParams hp = heavy_params(pl, pl->state_eval.p, sum, 0, 0);
   CU(launch_heavy(pl, sum, hp, (int)pl->items.size(), pl->stream));
   FinalizeParams fp{};
@@ -1188,7 +1274,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, 
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(pl->h_state, pl->state_eval.p, sizeof(FitState), cudaMemcpyDeviceToHost, pl->stream));
   CU(cudaStreamSynchronize(pl->stream));
-  if (loss) *loss = pl->h_state->last_loss;
+  if (loss) *loss = (double)pl->h_state->last_loss;
   if (dg_r)
     if (int r = download_unpadded(pl, pl->ggrad_r.p, dg_r, (size_t)pl->nants)) return r;
   if (dg_i)
@@ -1198,8 +1284,16 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, float prior_r, 
   return 0;
 }
 
-int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, calb2_fit_result* res) {
+int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, calb2_fit_result* res) {
   if (!pl || !o || !res) return fail(CALB2_ERR_ARG, "null argument");
+  if (pl->gen) {
+    if (o->optimizer < 0 || o->optimizer > CALB2_OPT_FTRL) return fail(CALB2_ERR_ARG, "unknown optimizer id %d", o->optimizer);
+    if (o->maxsteps < 0 || o->n_profile_steps < 0) return fail(CALB2_ERR_ARG, "negative step count");
+    if (o->maxsteps > 0 && !loss_history_v) return fail(CALB2_ERR_ARG, "loss_history is null");
+    CU(cudaSetDevice(pl->device));
+    return pl->gen->fit(o, loss_history_v, res);
+  }
+  float* loss_history = (float*)loss_history_v;
   if (!pl->have_data || !pl->have_gains || !pl->have_coeffs) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
   if (o->optimizer < 0 || o->optimizer > CALB2_OPT_FTRL) return fail(CALB2_ERR_ARG, "unknown optimizer id %d", o->optimizer);
   if (o->maxsteps < 0 || o->n_profile_steps < 0) return fail(CALB2_ERR_ARG, "negative step count");
@@ -1215,23 +1309,23 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, float* loss_history, c
     if (int r = ensure_grad_buffers(pl)) return r;
   FitConsts k{};
   k.optimizer = o->optimizer;
-  k.lr = o->learning_rate;
-  k.beta1 = o->beta_1;
-  k.beta2 = o->beta_2;
-  k.eps = o->epsilon;
-  k.rho = o->rho;
-  k.momentum = o->momentum;
-  k.init_acc = o->initial_accumulator_value;
-  k.l1 = o->l1_regularization_strength;
-  k.l2 = o->l2_regularization_strength;
-  k.lr_power = o->learning_rate_power;
+  k.lr = (float)o->learning_rate;
+  k.beta1 = (float)o->beta_1;
+  k.beta2 = (float)o->beta_2;
+  k.eps = (float)o->epsilon;
+  k.rho = (float)o->rho;
+  k.momentum = (float)o->momentum;
+  k.init_acc = (float)o->initial_accumulator_value;
+  k.l1 = (float)o->l1_regularization_strength;
+  k.l2 = (float)o->l2_regularization_strength;
+  k.lr_power = (float)o->learning_rate_power;
   k.nesterov = o->nesterov;
   k.maxsteps = o->maxsteps;
   k.tol = o->tol;
   k.use_min = o->use_min;
   k.regularization = o->regularization;
-  k.prior_r = o->prior_r_sum;
-  k.prior_i = o->prior_i_sum;
+  k.prior_r = (float)o->prior_r_sum;
+  k.prior_i = (float)o->prior_i_sum;
   k.n_skip = o->n_profile_steps + 1;
   const long long total = (long long)k.n_skip + o->maxsteps;
 
@@ -1415,6 +1509,7 @@ int calb2_comm_init(calb2_plan* pl, const void* id, int32_t rank, int32_t nranks
   if (!pl || !id) return fail(CALB2_ERR_ARG, "null argument");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(CALB2_ERR_ARG, "bad rank/nranks");
   if (nranks == 1) return 0;
+  if (pl->gen) return fail(CALB2_ERR_UNSUPPORTED, "the generic (float64 / oversized-group) path runs on one GPU");
   if (int r = load_nccl(nccl_lib)) return r;
   CU(cudaSetDevice(pl->device));
   IdBlob blob;
@@ -1440,6 +1535,7 @@ static size_t xbuf_bytes(const calb2_plan* pl) {
 
 int calb2_comm_peer_export(calb2_plan* pl, void* ipc_handle_out) {
   if (!pl || !ipc_handle_out) return fail(CALB2_ERR_ARG, "null argument");
+  if (pl->gen) return fail(CALB2_ERR_UNSUPPORTED, "the generic (float64 / oversized-group) path runs on one GPU");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
   CU(cudaSetDevice(pl->device));
   if (!pl->xbuf) {

@@ -223,75 +223,106 @@ __device__ __forceinline__ void axpy4(float c, const float4& a, float4& v) {
 // ------------------------------------------------------------------------------------------------
 enum { OPT_ADAMAX = 0, OPT_ADAM = 1, OPT_SGD = 2, OPT_RMSPROP = 3, OPT_ADAGRAD = 4, OPT_ADADELTA = 5, OPT_NADAM = 6, OPT_FTRL = 7 };
 
+// float / double overloads so the optimizer rules below are written once for both precisions
+__device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float m_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float m_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double m_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float m_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double m_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float m_pow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double m_pow(double a, double b) { return pow(a, b); }
+
 // One parameter, one step.  m / u are the parameter's two optimizer slots:
 //   Adamax, Adam, Nadam: first / second moment      SGD: momentum accumulator (m)        RMSprop: momentum (m), rms (u)
 //   Adagrad: accumulator (u, starts at initial_accumulator_value)                         Adadelta: accum (m), accum_update (u)
 //   Ftrl: accumulator (m, starts at initial_accumulator_value), linear (u)
-template <bool SPARSE>
-__device__ __forceinline__ float opt_step(const FitConsts& k, const FitState* st, float theta, float g, float& m, float& u,
-                                          float lr_t) {
+// K / S are the hyper-parameter and state structs of the precision T (FitConsts / FitState for float32).
+template <bool SPARSE, class T, class K, class S>
+__device__ __forceinline__ T opt_step(const K& k, const S* st, T theta, T g, T& m, T& u, T lr_t) {
+  const T one = (T)1;
   switch (k.optimizer) {
     case OPT_ADAMAX:
-      m = SPARSE ? (m * k.beta1 + g * (1.f - k.beta1)) : (m + (g - m) * (1.f - k.beta1));
-      u = fmaxf(u * k.beta2, fabsf(g));
+      m = SPARSE ? (m * k.beta1 + g * (one - k.beta1)) : (m + (g - m) * (one - k.beta1));
+      u = m_max(u * k.beta2, m_abs(g));
       return theta - lr_t * (m / (u + k.eps));
     case OPT_ADAM:
-      m = SPARSE ? (m * k.beta1 + g * (1.f - k.beta1)) : (m + (g - m) * (1.f - k.beta1));
-      u = SPARSE ? (u * k.beta2 + (g * g) * (1.f - k.beta2)) : (u + (g * g - u) * (1.f - k.beta2));
-      return theta - (m * lr_t) / (sqrtf(u) + k.eps);
+      m = SPARSE ? (m * k.beta1 + g * (one - k.beta1)) : (m + (g - m) * (one - k.beta1));
+      u = SPARSE ? (u * k.beta2 + (g * g) * (one - k.beta2)) : (u + (g * g - u) * (one - k.beta2));
+      return theta - (m * lr_t) / (m_sqrt(u) + k.eps);
     case OPT_SGD:  // ApplyGradientDescent / ApplyKerasMomentum
-      if (k.momentum == 0.f) return theta - lr_t * g;
+      if (k.momentum == (T)0) return theta - lr_t * g;
       m = m * k.momentum - lr_t * g;
       return k.nesterov ? theta + m * k.momentum - lr_t * g : theta + m;
     case OPT_RMSPROP:  // centered = False
-      u = k.rho * u + (1.f - k.rho) * (g * g);
-      if (k.momentum > 0.f) {  // fused ApplyRMSProp: epsilon inside the square root
-        m = k.momentum * m + lr_t * g * rsqrtf(u + k.eps);
+      u = k.rho * u + (one - k.rho) * (g * g);
+      if (k.momentum > (T)0) {  // fused ApplyRMSProp: epsilon inside the square root
+        m = k.momentum * m + lr_t * g * m_rsqrt(u + k.eps);
         return theta - m;
       }
-      return theta - lr_t * g / (sqrtf(u) + k.eps);
+      return theta - lr_t * g / (m_sqrt(u) + k.eps);
     case OPT_ADAGRAD:  // ApplyAdagradV2
       u = u + g * g;
-      return theta - lr_t * g / (sqrtf(u) + k.eps);
+      return theta - lr_t * g / (m_sqrt(u) + k.eps);
     case OPT_ADADELTA: {  // ApplyAdadelta
-      m = m * k.rho + (g * g) * (1.f - k.rho);
-      const float upd = sqrtf(u + k.eps) * rsqrtf(m + k.eps) * g;
-      u = u * k.rho + (upd * upd) * (1.f - k.rho);
+      m = m * k.rho + (g * g) * (one - k.rho);
+      const T upd = m_sqrt(u + k.eps) * m_rsqrt(m + k.eps) * g;
+      u = u * k.rho + (upd * upd) * (one - k.rho);
       return theta - upd * lr_t;
     }
     case OPT_NADAM: {  // Keras Nadam: aux = {1 - m_schedule_new, 1 - m_schedule_next, 1 - u_t, u_{t+1}}, aux2[0] = 1 - beta_2^t
-      const float g_prime = g / st->aux[0];
-      m = k.beta1 * m + (1.f - k.beta1) * g;
-      const float m_prime = m / st->aux[1];
-      u = k.beta2 * u + (1.f - k.beta2) * (g * g);
-      const float v_prime = u / st->aux2[0];
-      const float m_bar = st->aux[2] * g_prime + st->aux[3] * m_prime;
-      return theta - lr_t * m_bar / (sqrtf(v_prime) + k.eps);
+      const T g_prime = g / st->aux[0];
+      m = k.beta1 * m + (one - k.beta1) * g;
+      const T m_prime = m / st->aux[1];
+      u = k.beta2 * u + (one - k.beta2) * (g * g);
+      const T v_prime = u / st->aux2[0];
+      const T m_bar = st->aux[2] * g_prime + st->aux[3] * m_prime;
+      return theta - lr_t * m_bar / (m_sqrt(v_prime) + k.eps);
     }
     default: {  // OPT_FTRL, ApplyFtrlV2 without shrinkage
-      const float acc_new = m + g * g;
-      const bool half = k.lr_power == -0.5f;
-      const float p_new = half ? sqrtf(acc_new) : powf(acc_new, -k.lr_power);
-      const float p_old = half ? sqrtf(m) : powf(m, -k.lr_power);
+      const T acc_new = m + g * g;
+      const bool half = k.lr_power == (T)-0.5;
+      const T p_new = half ? m_sqrt(acc_new) : m_pow(acc_new, -k.lr_power);
+      const T p_old = half ? m_sqrt(m) : m_pow(m, -k.lr_power);
       u += g - (p_new - p_old) / lr_t * theta;
-      const float quadratic = p_new / lr_t + 2.f * k.l2;
+      const T quadratic = p_new / lr_t + (T)2 * k.l2;
       m = acc_new;
-      const float sgn = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
-      return fabsf(u) > k.l1 ? (sgn * k.l1 - u) / quadratic : 0.f;
+      const T sgn = u > (T)0 ? one : (u < (T)0 ? -one : (T)0);
+      return m_abs(u) > k.l1 ? (sgn * k.l1 - u) / quadratic : (T)0;
     }
   }
 }
 
 // Keras local_step = iterations + 1; powers evaluated in double and rounded once (identical in every kernel)
-__device__ __forceinline__ float bias_corrected_lr(const FitConsts& k, int step) {
+template <class T, class K>
+__device__ __forceinline__ T bias_corrected_lr_t(const K& k, int step) {
   const double tt = (double)(step + 1);
-  if (k.optimizer == OPT_ADAMAX) return k.lr / (1.f - (float)pow((double)k.beta1, tt));
+  if (k.optimizer == OPT_ADAMAX) return k.lr / ((T)1 - (T)pow((double)k.beta1, tt));
   if (k.optimizer == OPT_ADAM) {
-    const float b1p = (float)pow((double)k.beta1, tt);
-    const float b2p = (float)pow((double)k.beta2, tt);
-    return k.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    const T b1p = (T)pow((double)k.beta1, tt);
+    const T b2p = (T)pow((double)k.beta2, tt);
+    return k.lr * m_sqrt((T)1 - b2p) / ((T)1 - b1p);
   }
   return k.lr;
+}
+__device__ __forceinline__ float bias_corrected_lr(const FitConsts& k, int step) { return bias_corrected_lr_t<float>(k, step); }
+
+// per-step scalars of the Nadam momentum schedule (Keras Nadam._prepare_local, decay 0.004), kept in the fit state
+template <class T, class K, class S>
+__device__ __forceinline__ void nadam_schedule(const K& k, S* st, int t) {
+  const double ls = (double)(t + 1);
+  const T u_t = k.beta1 * ((T)1 - (T)0.5 * (T)pow(0.96, 0.004 * ls));
+  const T u_t1 = k.beta1 * ((T)1 - (T)0.5 * (T)pow(0.96, 0.004 * (ls + 1.0)));
+  const T ms_new = (T)(t == 0 ? 1.0 : st->m_schedule) * u_t;
+  const T ms_next = ms_new * u_t1;
+  st->m_schedule = (double)ms_new;
+  st->aux[0] = (T)1 - ms_new;
+  st->aux[1] = (T)1 - ms_next;
+  st->aux[2] = (T)1 - u_t;
+  st->aux[3] = u_t1;
+  st->aux2[0] = (T)1 - (T)pow((double)k.beta2, ls);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -697,8 +728,8 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
       if (ci >= 0) {
         const float2 g = *reinterpret_cast<const float2*>(rowdc + r * 2);
         float mr = p.cm_r[ci], ur = p.cu_r[ci], mi = p.cm_i[ci], ui = p.cu_i[ci];
-        const float nr = opt_step<false>(p.k, st, p.c_r_rw[ci], g.x, mr, ur, lr_fused);
-        const float ni = opt_step<false>(p.k, st, p.c_i_rw[ci], g.y, mi, ui, lr_fused);
+        const float nr = opt_step<false, float>(p.k, st, p.c_r_rw[ci], g.x, mr, ur, lr_fused);
+        const float ni = opt_step<false, float>(p.k, st, p.c_i_rw[ci], g.y, mi, ui, lr_fused);
         p.cm_r[ci] = mr;
         p.cu_r[ci] = ur;
         p.cm_i[ci] = mi;
@@ -817,19 +848,7 @@ __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams 
 
   const int t = st->step;
   st->lr_t = bias_corrected_lr(p.k, t);
-  if (p.k.optimizer == OPT_NADAM) {  // Keras Nadam._prepare_local: momentum schedule with decay 0.004
-    const double ls = (double)(t + 1);
-    const float u_t = p.k.beta1 * (1.f - 0.5f * (float)pow(0.96, 0.004 * ls));
-    const float u_t1 = p.k.beta1 * (1.f - 0.5f * (float)pow(0.96, 0.004 * (ls + 1.0)));
-    const float ms_new = (float)(t == 0 ? 1.0 : st->m_schedule) * u_t;
-    const float ms_next = ms_new * u_t1;
-    st->m_schedule = (double)ms_new;
-    st->aux[0] = 1.f - ms_new;
-    st->aux[1] = 1.f - ms_next;
-    st->aux[2] = 1.f - u_t;
-    st->aux[3] = u_t1;
-    st->aux2[0] = 1.f - (float)pow((double)p.k.beta2, ls);
-  }
+  if (p.k.optimizer == OPT_NADAM) nadam_schedule<float>(p.k, st, t);
   int snap = 0;
   const int rec = t - p.k.n_skip;
   if (rec >= 0) {
@@ -1017,8 +1036,8 @@ __global__ void __launch_bounds__(GK_THREADS) gains_kernel(const GainsParams p) 
   for (int c = 0; c < 2; ++c) {
     const size_t oc = o + c;
     float mr = p.m_r[oc], ur = p.u_r[oc], mi = p.m_i[oc], ui = p.u_i[oc];
-    const float nr = opt_step<true>(p.k, st, gr[oc], a_r[c], mr, ur, lr_t);
-    const float ni = opt_step<true>(p.k, st, gi[oc], a_i[c], mi, ui, lr_t);
+    const float nr = opt_step<true, float>(p.k, st, gr[oc], a_r[c], mr, ur, lr_t);
+    const float ni = opt_step<true, float>(p.k, st, gi[oc], a_i[c], mi, ui, lr_t);
     p.m_r[oc] = mr;
     p.u_r[oc] = ur;
     p.m_i[oc] = mi;
@@ -1186,8 +1205,8 @@ __global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
   }
   if (p.mode == 1) return;
   float mr = p.m_r[c], ur = p.u_r[c], mi = p.m_i[c], ui = p.u_i[c];
-  const float nr = opt_step<false>(p.k, st, p.c_r[c], gr, mr, ur, st->lr_t);
-  const float ni = opt_step<false>(p.k, st, p.c_i[c], gi, mi, ui, st->lr_t);
+  const float nr = opt_step<false, float>(p.k, st, p.c_r[c], gr, mr, ur, st->lr_t);
+  const float ni = opt_step<false, float>(p.k, st, p.c_i[c], gi, mi, ui, st->lr_t);
   p.m_r[c] = mr;
   p.u_r[c] = ur;
   p.m_i[c] = mi;

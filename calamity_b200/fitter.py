@@ -27,6 +27,10 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _dtype_name(dt):
+    return {np.dtype(np.float32): "float32", np.dtype(np.float64): "float64"}[np.dtype(dt)]
+
+
 class FitPlan:
     """Device-resident basis + per-integration state.  Mirrors calibration.py:1143-1152 (create) and
     the per-integration calls of 1184-1300."""
@@ -34,16 +38,20 @@ class FitPlan:
     def __init__(self, layout, device=0, tile_freqs=0, basis_batch=2048):
         self._lib = nat.load()
         self.layout = layout
+        # float32: the fused sm_100a kernels; float64 (precision=64): the generic device path
+        self.dtype = np.dtype(getattr(layout, "dtype", np.float32))
+        if self.dtype not in nat.DTYPE_IDS:
+            raise TypeError(f"unsupported dtype {self.dtype}; float32 or float64")
         self._handle = C.c_void_p()
         desc = nat.PlanDesc(
             device=device, nants=layout.nants, nfreqs=layout.nfreqs, ngroups=layout.ngroups,
             group_ncomp=nat.iptr(layout.group_ncomp), group_nslots=nat.iptr(layout.group_nslots),
             slot_nbls=nat.iptr(layout.slot_nbls), bl_ant0=nat.iptr(layout.bl_ant0), bl_ant1=nat.iptr(layout.bl_ant1),
-            tile_freqs=tile_freqs,
+            tile_freqs=tile_freqs, dtype=nat.DTYPE_IDS[self.dtype],
         )
         nat.check(self._lib.calb2_plan_create(C.byref(desc), C.byref(self._handle)))
         for g0 in range(0, layout.ngroups, basis_batch):
-            blks = layout.blocks[g0 : g0 + basis_batch]
+            blks = [np.ascontiguousarray(b, dtype=self.dtype) for b in layout.blocks[g0 : g0 + basis_batch]]
             ptrs = (C.c_void_p * len(blks))(*[b.ctypes.data if b.size else None for b in blks])
             nat.check(self._lib.calb2_plan_set_basis(self._handle, g0, len(blks), ptrs))
         info = nat.PlanInfo()
@@ -69,30 +77,36 @@ class FitPlan:
         self.close()
 
     # -- per integration
+    def _arr(self, a):
+        return np.ascontiguousarray(a, dtype=self.dtype)
+
+    def _ptr(self, a):
+        return nat.fptr(a, self.dtype)
+
     def set_integration(self, data_r, data_i, wgts):
-        d_r, d_i, w = _f32(data_r), _f32(data_i), _f32(wgts)
+        d_r, d_i, w = self._arr(data_r), self._arr(data_i), self._arr(wgts)
         assert d_r.shape == (self.layout.nbls, self.layout.nfreqs), d_r.shape
-        nat.check(self._lib.calb2_set_integration(self._handle, nat.fptr(d_r), nat.fptr(d_i), nat.fptr(w)))
+        nat.check(self._lib.calb2_set_integration(self._handle, self._ptr(d_r), self._ptr(d_i), self._ptr(w)))
 
     def set_gains(self, g_r, g_i):
-        g_r, g_i = _f32(g_r), _f32(g_i)
+        g_r, g_i = self._arr(g_r), self._arr(g_i)
         assert g_r.shape == (self.layout.nants, self.layout.nfreqs), g_r.shape
-        nat.check(self._lib.calb2_set_gains(self._handle, nat.fptr(g_r), nat.fptr(g_i)))
+        nat.check(self._lib.calb2_set_gains(self._handle, self._ptr(g_r), self._ptr(g_i)))
 
     def set_coeffs(self, coef_r, coef_i):
-        c_r, c_i = _f32(coef_r), _f32(coef_i)
+        c_r, c_i = self._arr(coef_r), self._arr(coef_i)
         assert c_r.shape == (self.layout.ncoef,), c_r.shape
-        nat.check(self._lib.calb2_set_coeffs(self._handle, nat.fptr(c_r), nat.fptr(c_i)))
+        nat.check(self._lib.calb2_set_coeffs(self._handle, self._ptr(c_r), self._ptr(c_i)))
 
     def init_coeffs(self, sky_r, sky_i):
-        s_r, s_i = _f32(sky_r), _f32(sky_i)
-        nat.check(self._lib.calb2_init_coeffs(self._handle, nat.fptr(s_r), nat.fptr(s_i)))
+        s_r, s_i = self._arr(sky_r), self._arr(sky_i)
+        nat.check(self._lib.calb2_init_coeffs(self._handle, self._ptr(s_r), self._ptr(s_i)))
 
     def prior_sums(self, sky_r, sky_i):
-        s_r, s_i = _f32(sky_r), _f32(sky_i)
-        pr, pi = C.c_float(), C.c_float()
-        nat.check(self._lib.calb2_prior_sums(self._handle, nat.fptr(s_r), nat.fptr(s_i), C.byref(pr), C.byref(pi)))
-        return np.float32(pr.value), np.float32(pi.value)
+        s_r, s_i = self._arr(sky_r), self._arr(sky_i)
+        pr, pi = C.c_double(), C.c_double()
+        nat.check(self._lib.calb2_prior_sums(self._handle, self._ptr(s_r), self._ptr(s_i), C.byref(pr), C.byref(pi)))
+        return self.dtype.type(pr.value), self.dtype.type(pi.value)
 
     def apply_model_snr_weights(self):
         nat.check(self._lib.calb2_apply_model_snr_weights(self._handle))
@@ -123,46 +137,46 @@ class FitPlan:
             l2_regularization_strength=hp.get("l2_regularization_strength", 0.0),
             learning_rate_power=hp.get("learning_rate_power", 0.0), nesterov=int(bool(hp.get("nesterov", False))),
         )
-        hist = np.zeros(max(1, int(maxsteps)), dtype=np.float32)
+        hist = np.zeros(max(1, int(maxsteps)), dtype=self.dtype)
         res = nat.FitResult()
-        nat.check(self._lib.calb2_fit(self._handle, C.byref(opts), nat.fptr(hist), C.byref(res)))
+        nat.check(self._lib.calb2_fit(self._handle, C.byref(opts), self._ptr(hist), C.byref(res)))
         result = {name: getattr(res, name) for name, _ in nat.FitResult._fields_}
         return hist[: res.nsteps_recorded].copy(), result
 
     def loss_and_grads(self, model_regularization=None, prior_r_sum=0.0, prior_i_sum=0.0):
         lay = self.layout
-        loss = C.c_float()
-        dg_r = np.zeros((lay.nants, lay.nfreqs), dtype=np.float32)
+        loss = C.c_double()
+        dg_r = np.zeros((lay.nants, lay.nfreqs), dtype=self.dtype)
         dg_i = np.zeros_like(dg_r)
-        dc_r = np.zeros(lay.ncoef, dtype=np.float32)
+        dc_r = np.zeros(lay.ncoef, dtype=self.dtype)
         dc_i = np.zeros_like(dc_r)
         nat.check(self._lib.calb2_loss_and_grads(
             self._handle, 1 if model_regularization == "sum" else 0, float(prior_r_sum), float(prior_i_sum),
-            C.byref(loss), nat.fptr(dg_r), nat.fptr(dg_i), nat.fptr(dc_r), nat.fptr(dc_i)))
-        return np.float32(loss.value), dg_r, dg_i, dc_r, dc_i
+            C.byref(loss), self._ptr(dg_r), self._ptr(dg_i), self._ptr(dc_r), self._ptr(dc_i)))
+        return self.dtype.type(loss.value), dg_r, dg_i, dc_r, dc_i
 
     # -- results
     def get_gains(self):
-        g_r = np.zeros((self.layout.nants, self.layout.nfreqs), dtype=np.float32)
+        g_r = np.zeros((self.layout.nants, self.layout.nfreqs), dtype=self.dtype)
         g_i = np.zeros_like(g_r)
-        nat.check(self._lib.calb2_get_gains(self._handle, nat.fptr(g_r), nat.fptr(g_i)))
+        nat.check(self._lib.calb2_get_gains(self._handle, self._ptr(g_r), self._ptr(g_i)))
         return g_r, g_i
 
     def get_coeffs(self):
-        c_r = np.zeros(self.layout.ncoef, dtype=np.float32)
+        c_r = np.zeros(self.layout.ncoef, dtype=self.dtype)
         c_i = np.zeros_like(c_r)
-        nat.check(self._lib.calb2_get_coeffs(self._handle, nat.fptr(c_r), nat.fptr(c_i)))
+        nat.check(self._lib.calb2_get_coeffs(self._handle, self._ptr(c_r), self._ptr(c_i)))
         return c_r, c_i
 
     def get_model(self):
-        m_r = np.zeros((self.layout.nbls, self.layout.nfreqs), dtype=np.float32)
+        m_r = np.zeros((self.layout.nbls, self.layout.nfreqs), dtype=self.dtype)
         m_i = np.zeros_like(m_r)
-        nat.check(self._lib.calb2_get_model(self._handle, nat.fptr(m_r), nat.fptr(m_i)))
+        nat.check(self._lib.calb2_get_model(self._handle, self._ptr(m_r), self._ptr(m_i)))
         return m_r, m_i
 
     def get_weights(self):
-        w = np.zeros((self.layout.nbls, self.layout.nfreqs), dtype=np.float32)
-        nat.check(self._lib.calb2_get_weights(self._handle, nat.fptr(w)))
+        w = np.zeros((self.layout.nbls, self.layout.nfreqs), dtype=self.dtype)
+        nat.check(self._lib.calb2_get_weights(self._handle, self._ptr(w)))
         return w
 
     # -- multi-GPU

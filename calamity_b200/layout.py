@@ -11,9 +11,10 @@ import numpy as np
 
 
 class RaggedLayout:
-    def __init__(self, nants, nfreqs):
+    def __init__(self, nants, nfreqs, dtype=np.float32):
         self.nants = int(nants)
         self.nfreqs = int(nfreqs)
+        self.dtype = np.dtype(dtype)  # element type of the basis blocks and of the plan built from this layout
         self.group_ncomp = []
         self.group_nslots = []
         self.slot_nbls = []
@@ -50,9 +51,9 @@ class RaggedLayout:
         return self
 
     @classmethod
-    def from_chunked_dict(cls, chunked, ants_map, nfreqs, nants=None):
+    def from_chunked_dict(cls, chunked, ants_map, nfreqs, nants=None, dtype=np.float32):
         """`chunked` is the output of chunk_fg_comp_dict_by_nbls: {(nbl, nvecs): {fit_grp: [nrg*nfreqs, ncomp]}}."""
-        lay = cls(len(ants_map) if nants is None else nants, nfreqs)
+        lay = cls(len(ants_map) if nants is None else nants, nfreqs, dtype=dtype)
         cache = {}
         for (nbls, nvecs), grp_dict in chunked.items():
             lay.chunks.append(dict(nvecs=int(nvecs), ngrps=len(grp_dict), nbls=int(nbls), group0=len(lay.blocks)))
@@ -61,17 +62,17 @@ class RaggedLayout:
                 if key not in cache:
                     nrg = len(fit_grp)
                     blk = np.asarray(vecs).reshape(nrg, nfreqs, vecs.shape[1]).transpose(0, 2, 1)
-                    cache[key] = (np.ascontiguousarray(blk, dtype=np.float32), vecs)  # keep vecs alive: id() is reused otherwise
+                    cache[key] = (np.ascontiguousarray(blk, dtype=lay.dtype), vecs)  # keep vecs alive: id() is reused otherwise
                 slots = [[(ants_map[ap[0]], ants_map[ap[1]]) for ap in red] for red in fit_grp]
                 lay._add_group(cache[key][0], slots)
         return lay._finalize()
 
     @classmethod
-    def from_dense(cls, fg_comps, corr_inds, nants):
+    def from_dense(cls, fg_comps, corr_inds, nants, dtype=np.float32):
         """Reference tensors [nvecs, ngrps, nbls, nfreqs] + corr_inds.  Trailing all-zero rows are dropped
         (they never change the model nor receive gradient); every baseline becomes its own slot."""
         nfreqs = int(np.shape(fg_comps[0])[3])
-        lay = cls(nants, nfreqs)
+        lay = cls(nants, nfreqs, dtype=dtype)
         for comps, chunk in zip(fg_comps, corr_inds):
             comps = np.asarray(comps)
             nvecs, ngrps, nbls, _ = comps.shape
@@ -80,15 +81,15 @@ class RaggedLayout:
                 rows = comps[:, g]
                 live = np.where(np.any(rows.reshape(nvecs, -1) != 0, axis=1))[0]
                 ncomp = int(live.max()) + 1 if len(live) else 0
-                blk = np.ascontiguousarray(rows[:ncomp].transpose(1, 0, 2), dtype=np.float32)
+                blk = np.ascontiguousarray(rows[:ncomp].transpose(1, 0, 2), dtype=lay.dtype)
                 lay._add_group(blk, [[(int(i), int(j))] for (i, j) in chunk[g]])
         return lay._finalize()
 
     # ------------------------------------------------------------------ reference-shape <-> flat
     def flatten_data(self, chunk_tensors):
-        """list of [ngrps, nbls, nfreqs] -> float32 [nbls_total, nfreqs] in canonical baseline order."""
+        """list of [ngrps, nbls, nfreqs] -> [nbls_total, nfreqs] (layout dtype) in canonical baseline order."""
         return np.ascontiguousarray(
-            np.concatenate([np.asarray(t, dtype=np.float32).reshape(-1, self.nfreqs) for t in chunk_tensors], axis=0)
+            np.concatenate([np.asarray(t, dtype=self.dtype).reshape(-1, self.nfreqs) for t in chunk_tensors], axis=0)
         )
 
     def unflatten_data(self, flat, dtype=np.float32):
@@ -100,8 +101,8 @@ class RaggedLayout:
         return out
 
     def flatten_coeffs(self, chunk_coeffs):
-        """list of [nvecs, ngrps, 1, 1] -> float32 [ncoef]."""
-        flat = np.zeros(self.ncoef, dtype=np.float32)
+        """list of [nvecs, ngrps, 1, 1] -> [ncoef] (layout dtype)."""
+        flat = np.zeros(self.ncoef, dtype=self.dtype)
         for ch, t in zip(self.chunks, chunk_coeffs):
             t = np.asarray(t).reshape(ch["nvecs"], ch["ngrps"])
             for g in range(ch["ngrps"]):

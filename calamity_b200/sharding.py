@@ -38,7 +38,7 @@ class Shard:
         self.bl1 = self.bl0 + int(np.sum(full.slot_nbls[slot0:slot1]))
         self.coef0 = int(full.group_coef0[g0])
         self.coef1 = int(full.group_coef0[g1])
-        lay = RaggedLayout(full.nants, full.nfreqs)
+        lay = RaggedLayout(full.nants, full.nfreqs, dtype=full.dtype)
         lay.group_ncomp = full.group_ncomp[g0:g1]
         lay.group_nslots = full.group_nslots[g0:g1]
         lay.slot_nbls = full.slot_nbls[slot0:slot1]

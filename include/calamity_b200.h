@@ -9,8 +9,14 @@
  * Conventions: plain C, every function returns 0 on success and a negative code on failure
  * (`calb2_last_error()` gives the message of the calling thread's last failure); no exception crosses
  * the ABI; the caller owns every host buffer, the library owns all device memory; a plan is bound to
- * one device and must be driven by one host thread at a time.  All floating point buffers are IEEE
- * float32 (the reference's default `dtype=np.float32`, calibration.py:974), all indices int32.
+ * one device and must be driven by one host thread at a time.  Floating point buffers are IEEE float32
+ * (the reference's default `dtype=np.float32`, calibration.py:974) or float64 (`--precision 64`, calibration.py:1795),
+ * as chosen once in calb2_plan_desc.dtype: every `const void*` / `void*` array argument below then points at
+ * elements of that type.  All indices are int32.
+ *
+ * float32 plans run the fused sm_100a kernels.  float64 plans, and float32 plans with a fitting group too large
+ * for the fused kernel's staged tile (more than 704 basis vectors), run a generic unfused device path with the same
+ * arithmetic (single GPU only).
  *
  * Canonical orderings (they are exactly the reference's flattening of its chunked tensors):
  *   groups     : chunk-major, then group index inside the chunk        (calibration.py:165-170)
@@ -48,6 +54,9 @@ enum {
   CALB2_OPT_ADADELTA = 5, CALB2_OPT_NADAM = 6, CALB2_OPT_FTRL = 7
 };
 
+/* dtype of calibrate_and_model_tensor (calibration.py:974): element type of a plan's floating point buffers. */
+enum { CALB2_F32 = 0, CALB2_F64 = 1 };
+
 /* model_regularization of calibration.py:619-661: anything but "sum" is the plain chi-squared. */
 enum { CALB2_REG_NONE = 0, CALB2_REG_SUM = 1 };
 
@@ -64,22 +73,24 @@ typedef struct {
   const int32_t* bl_ant0;       /* [nbls_total] corr_inds[..][0] in canonical order */
   const int32_t* bl_ant1;       /* [nbls_total] corr_inds[..][1] */
   int32_t tile_freqs;        /* 0 = choose; else 16, 32 or 64 channels per staged tile */
+  int32_t dtype;             /* CALB2_F32 or CALB2_F64: element type of every floating point buffer of this plan */
 } calb2_plan_desc;
 
 /* Options of fit_gains_and_foregrounds (calibration.py:447-473). */
 typedef struct {
   int32_t optimizer;         /* CALB2_OPT_*            (`optimizer`, calibration.py:460, 571) */
-  float learning_rate;       /* Keras names, forwarded verbatim by **opt_kwargs (calibration.py:472) */
-  float beta_1;
-  float beta_2;
-  float epsilon;
   int32_t maxsteps;          /* calibration.py:459, 699 */
+  double learning_rate;      /* Keras names, forwarded verbatim by **opt_kwargs (calibration.py:472); real-valued options
+                                are doubles and are rounded to the plan's dtype, as Keras casts them to the variable dtype */
+  double beta_1;
+  double beta_2;
+  double epsilon;
   double tol;                /* calibration.py:458, 712 */
   int32_t use_min;           /* calibration.py:457, 702-710 */
   int32_t freeze_model;      /* calibration.py:461, 598-603 */
   int32_t regularization;    /* CALB2_REG_*            (calibration.py:470, 619) */
-  float prior_r_sum;         /* sum(sky_model_r * wgts), calibration.py:620-625 */
-  float prior_i_sum;
+  double prior_r_sum;        /* sum(sky_model_r * wgts), calibration.py:620-625 */
+  double prior_i_sum;
   int32_t n_profile_steps;   /* extra real steps before the warm-up step (calibration.py:681-687) */
   int32_t steps_per_sync;    /* 0 = default; iterations enqueued between host checks of the stop flag */
   int32_t use_graph;         /* 1 = replay a captured CUDA graph of steps_per_sync iterations, -1 = never, 0 = automatic
@@ -88,13 +99,13 @@ typedef struct {
                                 single-slot and regularization is NONE); measured slower than the split step, default 0 */
   /* further Keras hyper-parameters (same names as the tf.keras.optimizers constructors); ignored by optimizers
    * that do not have them */
-  float rho;                         /* RMSprop, Adadelta */
-  float momentum;                    /* SGD, RMSprop */
-  float initial_accumulator_value;   /* Adagrad, Ftrl */
-  float l1_regularization_strength;  /* Ftrl */
-  float l2_regularization_strength;  /* Ftrl */
-  float learning_rate_power;         /* Ftrl */
-  int32_t nesterov;                  /* SGD */
+  double rho;                         /* RMSprop, Adadelta */
+  double momentum;                    /* SGD, RMSprop */
+  double initial_accumulator_value;   /* Adagrad, Ftrl */
+  double l1_regularization_strength;  /* Ftrl */
+  double l2_regularization_strength;  /* Ftrl */
+  double learning_rate_power;         /* Ftrl */
+  int32_t nesterov;                   /* SGD */
 } calb2_fit_options;
 
 typedef struct {
@@ -119,6 +130,8 @@ typedef struct {
   int32_t tile_freqs;
   int32_t rows_per_item_max;
   int64_t device_bytes;
+  int32_t generic;    /* 1: the plan runs the generic unfused path (float64, or a group too large for the fused tile) */
+  int32_t dtype;
 } calb2_plan_info;
 
 const char* calb2_last_error(void);
@@ -130,40 +143,40 @@ int calb2_plan_destroy(calb2_plan* plan);
 int calb2_plan_get_info(const calb2_plan* plan, calb2_plan_info* info);
 
 /* Upload basis vectors for groups [group_first, group_first + ngroups): blocks[i] points at the
- * group's float32 [nslots][ncomp][nfreqs] block (row k of slot s = fg_model_comps[c][k, g, b, :] for any
+ * group's [nslots][ncomp][nfreqs] block (plan dtype) (row k of slot s = fg_model_comps[c][k, g, b, :] for any
  * baseline b of slot s, calibration.py:178-183).  Equal pointers are uploaded once. */
-int calb2_plan_set_basis(calb2_plan* plan, int32_t group_first, int32_t ngroups, const float* const* blocks);
+int calb2_plan_set_basis(calb2_plan* plan, int32_t group_first, int32_t ngroups, const void* const* blocks);
 
 /* Per integration: mirrors tensorize_data's outputs (calibration.py:1184-1194), [nbls_total][nfreqs]. */
-int calb2_set_integration(calb2_plan* plan, const float* data_r, const float* data_i, const float* wgts);
+int calb2_set_integration(calb2_plan* plan, const void* data_r, const void* data_i, const void* wgts);
 /* tensorize_gains outputs (calibration.py:1213) [nants][nfreqs]; coefficient vectors [n_c_nz]. */
-int calb2_set_gains(calb2_plan* plan, const float* g_r, const float* g_i);
-int calb2_set_coeffs(calb2_plan* plan, const float* coef_r, const float* coef_i);
+int calb2_set_gains(calb2_plan* plan, const void* g_r, const void* g_i);
+int calb2_set_coeffs(calb2_plan* plan, const void* coef_r, const void* coef_i);
 
 /* tensorize_fg_coeffs (calibration.py:828-913) run on the device for both parts at once: least squares
  * of (sky * (wgts != 0)) on each group's basis.  Uses the weights given to calb2_set_integration. */
-int calb2_init_coeffs(calb2_plan* plan, const float* sky_r, const float* sky_i);
+int calb2_init_coeffs(calb2_plan* plan, const void* sky_r, const void* sky_i);
 /* sum(sky_model * wgts) of calibration.py:620-625, reduced on the device. */
-int calb2_prior_sums(calb2_plan* plan, const float* sky_r, const float* sky_i, float* prior_r, float* prior_i);
+int calb2_prior_sums(calb2_plan* plan, const void* sky_r, const void* sky_i, double* prior_r, double* prior_i);
 /* use_model_snr_weights block, calibration.py:1235-1242: w <- w (v_r^2 + v_i^2) / sum. */
 int calb2_apply_model_snr_weights(calb2_plan* plan);
 
 /* The loop of fit_gains_and_foregrounds, calibration.py:571-738.  loss_history has room for
  * opts->maxsteps floats; the first result->nsteps_recorded are filled (fit_history["loss"]). */
-int calb2_fit(calb2_plan* plan, const calb2_fit_options* opts, float* loss_history, calb2_fit_result* result);
+int calb2_fit(calb2_plan* plan, const calb2_fit_options* opts, void* loss_history, calb2_fit_result* result);
 
 /* One evaluation of loss and gradient at the current parameters without updating them (the
  * tape.gradient call of calibration.py:664-666); any output pointer may be NULL. */
-int calb2_loss_and_grads(calb2_plan* plan, int32_t regularization, float prior_r_sum, float prior_i_sum,
-                         float* loss, float* dg_r, float* dg_i, float* dcoef_r, float* dcoef_i);
+int calb2_loss_and_grads(calb2_plan* plan, int32_t regularization, double prior_r_sum, double prior_i_sum,
+                         double* loss, void* dg_r, void* dg_i, void* dcoef_r, void* dcoef_i);
 
 /* g_r_opt, g_i_opt, fg_r_opt, fg_i_opt of calibration.py:738. */
-int calb2_get_gains(calb2_plan* plan, float* g_r, float* g_i);
-int calb2_get_coeffs(calb2_plan* plan, float* coef_r, float* coef_i);
+int calb2_get_gains(calb2_plan* plan, void* g_r, void* g_i);
+int calb2_get_coeffs(calb2_plan* plan, void* coef_r, void* coef_i);
 /* Foreground model visibilities sum_k c_k A_k per baseline, [nbls_total][nfreqs]; the caller scatters
  * them into the [nants, nants, nfreqs] cube of yield_fg_model_array (calibration.py:402-444). */
-int calb2_get_model(calb2_plan* plan, float* model_r, float* model_i);
-int calb2_get_weights(calb2_plan* plan, float* wgts);
+int calb2_get_model(calb2_plan* plan, void* model_r, void* model_i);
+int calb2_get_weights(calb2_plan* plan, void* wgts);
 
 /* Multi-GPU: the plan holds one rank's share of the groups; the per-iteration
  * gain gradient, loss and regulariser sums are all-reduced over NCCL.  `nccl_unique_id` is the 128-byte

@@ -89,6 +89,19 @@ def test_calibrate_and_model_dpss(sky, noweights, perfect_data, use_min):
     assert all(isinstance(x, np.float32) for x in hist[0][0]["loss"])
 
 
+def test_calibrate_and_model_dpss_float64(sky):
+    """dtype=np.float64 (calibration.py:974; `--precision 64` of the CLI, 1795 / test_calibration.py:929): the fit runs
+    on the generic float64 device path, converges like the float32 one and returns float64 losses."""
+    sky_model, _ = sky
+    data = fx.add_noise_like_eor(sky_model)
+    gains = fx.randomized_gains(data)
+    model, resid, gains_out, hist = calibration.calibrate_and_model_dpss(
+        min_dly=2.0 / 0.3, offset=2.0 / 0.3, uvdata=data, gains=gains, verbose=False, use_redundancy=False, sky_model=None,
+        maxsteps=3000, tol=1e-10, correct_resid=True, correct_model=True, dtype=np.float64)
+    _ok(model, resid, data)
+    assert all(isinstance(x, np.float64) for x in hist[0][0]["loss"])
+
+
 @pytest.mark.parametrize("perfect_data, use_min", [(True, False), (False, True)])
 def test_calibrate_and_model_dpss_multitime(native_built, perfect_data, use_min):
     """test_calibration.py:466-516."""
