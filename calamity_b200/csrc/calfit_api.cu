@@ -149,6 +149,10 @@ struct calb2_plan {
   void* xpeer[CALB2_MAX_RANKS] = {nullptr};
   PeerView peers{};
   unsigned int xseq = 0;  // steps enqueued so far on the exchange (identical on all ranks)
+  DevBuf<unsigned int> tail_counter;
+  // the coefficient update runs on a second stream next to the gain update (they touch disjoint state)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t device_bytes = 0;
 };
 
@@ -329,6 +333,7 @@ static GainsParams gains_params(calb2_plan* pl, const FitState* st, const FitCon
   gp.sum = sum ? 1 : 0;
   gp.eval = eval;
   gp.peers.n = 0;
+  gp.tail_counter = nullptr;
   return gp;
 }
 
@@ -489,6 +494,22 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
   fp.xpar = 0;
   dim3 ggrid(pl->nants, (pl->nfp + GK_CH - 1) / GK_CH);
   const size_t ngrad = (size_t)2 * pl->nants * pl->nfp;
+  // The coefficient update only needs finalize's scalars and the fused kernel's backward sums: it is forked onto a second
+  // stream right after finalize_kernel and runs next to the gain-gradient reduce / exchange / gain update.
+  const bool need_coeffs = (!freeze && !fuse) || (k.use_min && !freeze);
+  bool forked = false;
+  auto fork_coeffs = [&]() -> int {
+    if (!need_coeffs) return 0;
+    CU(cudaEventRecord(pl->ev_fork, pl->stream));
+    CU(cudaStreamWaitEvent(pl->stream2, pl->ev_fork, 0));
+    // mode 0: optimizer step from the stored backward sums; mode 3: only the use_min snapshot copy
+    coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream2>>>(coeff_params(pl, pl->state.p, k, fuse ? 3 : 0, sum));
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(pl->ev_join, pl->stream2));
+    forked = true;
+    *launches += 1;
+    return 0;
+  };
   if (pl->nranks > 1 && pl->peers.n > 1) {
     // ---- exchange through peer memory (NVLink): no collective library call in the loop ----
     const unsigned int seq = pl->xseq++;
@@ -496,9 +517,6 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     unsigned int* my_flag = reinterpret_cast<unsigned int*>(pl->xbuf);
     double* my_scal = reinterpret_cast<double*>(pl->xbuf + XBUF_FLAG_BYTES) + par * 4;
     float* my_grad = reinterpret_cast<float*>(pl->xbuf + XBUF_FLAG_BYTES + XBUF_SCAL_BYTES) + (size_t)par * ngrad;
-    reduce_partials_kernel<<<1, 1024, 0, pl->stream>>>(partials, npartials, my_scal);
-    CU(cudaGetLastError());
-    CALB2_STAGE()
     fp.partials = nullptr;
     fp.nitems = 0;
     fp.peers = pl->peers;
@@ -510,32 +528,41 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     gupd.peers = pl->peers;
     gupd.xpar = par;
     if (!sum) {
-      // the local gradient partial does not need finalize's alpha / beta: publish scalars and gradient together
+      // The local gradient partial does not need finalize's alpha / beta.  One launch: gradient reduce, then its last
+      // CTA reduces the per-item partial sums into the exchange buffer and publishes scalars and gradient together.
+      gred.tail_counter = pl->tail_counter.p;
+      gred.tail_partials = partials;
+      gred.tail_npartials = npartials;
+      gred.tail_scal = my_scal;
+      gred.tail_flag = my_flag;
+      gred.tail_value = 2u * seq + 2u;
+      CALB2_STAGE()
       gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gred);
       CU(cudaGetLastError());
       CALB2_STAGE()
-      xpublish_kernel<<<1, 1, 0, pl->stream>>>(my_flag, 2u * seq + 2u);
-      CU(cudaGetLastError());
       fp.xwait = 2u * seq + 2u;
       CALB2_STAGE()
       finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
       CU(cudaGetLastError());
       CALB2_STAGE()
-      *launches += 2;
+      if (int r = fork_coeffs()) return r;
     } else {
       // 'sum' regulariser: alpha / beta need the global sums first (two publish / wait rounds per step)
+      reduce_partials_kernel<<<1, 1024, 0, pl->stream>>>(partials, npartials, my_scal);
+      CU(cudaGetLastError());
       xpublish_kernel<<<1, 1, 0, pl->stream>>>(my_flag, 2u * seq + 1u);
       CU(cudaGetLastError());
       fp.xwait = 2u * seq + 1u;
       finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
       CU(cudaGetLastError());
+      if (int r = fork_coeffs()) return r;
       gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gred);
       CU(cudaGetLastError());
       xpublish_kernel<<<1, 1, 0, pl->stream>>>(my_flag, 2u * seq + 2u);
       CU(cudaGetLastError());
       xwait_kernel<<<1, 32, 0, pl->stream>>>(pl->peers, 2u * seq + 2u, pl->state.p, 0);
       CU(cudaGetLastError());
-      *launches += 4;
+      *launches += 5;
     }
     gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gupd);
     CU(cudaGetLastError());
@@ -564,10 +591,12 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
       finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
       CU(cudaGetLastError());
       CALB2_STAGE()
+      if (int r = fork_coeffs()) return r;
     } else {
       if (int r = all_reduce(pl, pl->comm_scalars.p, 4, NCCL_FLOAT64)) return r;
       finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
       CU(cudaGetLastError());
+      if (int r = fork_coeffs()) return r;
       gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 1, sum, 0));
       CU(cudaGetLastError());
       // real and imaginary gradient tables are adjacent halves of one allocation
@@ -582,16 +611,11 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     fp.nitems = npartials;
     finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
     CU(cudaGetLastError());
+    if (int r = fork_coeffs()) return r;
     gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 0, sum, 0));
     CU(cudaGetLastError());
   }
-  if ((!freeze && !fuse) || (k.use_min && !freeze)) {
-    // mode 0: optimizer step from the stored backward sums; mode 3: only the use_min snapshot copy
-    coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(
-        coeff_params(pl, pl->state.p, k, fuse ? 3 : 0, sum));
-    CU(cudaGetLastError());
-    *launches += 1;
-  }
+  if (forked) CU(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));  // join: the next step reads the new coefficients
   CALB2_STAGE()
   *launches += 3;
   return 0;
@@ -862,6 +886,9 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
 #define TRY(x)          \
   if (!rc) rc = (x);
   CU(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&pl->stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
   if (generic) {
     TRY(upload(pl->d_slot_bl0, pl->slot_bl0, pl));
     TRY(upload(pl->d_bl_ant0, pl->bl_ant0, pl));
@@ -991,6 +1018,10 @@ int calb2_plan_destroy(calb2_plan* pl) {
   pl->sky_i.release();
   if (pl->h_staging) cudaFreeHost(pl->h_staging);
   if (pl->h_state) cudaFreeHost(pl->h_state);
+  pl->tail_counter.release();
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+  if (pl->stream2) cudaStreamDestroy(pl->stream2);
   if (pl->stream) cudaStreamDestroy(pl->stream);
   delete pl;
   return 0;
@@ -1573,6 +1604,10 @@ int calb2_comm_peer_import(calb2_plan* pl, const void* ipc_handles, int32_t rank
     pl->peers.grad[r] = reinterpret_cast<const float*>(base + ngrad_off);
   }
   pl->xseq = 0;
+  if (!pl->tail_counter.p) {
+    CU(pl->tail_counter.alloc(1));
+    CU(cudaMemset(pl->tail_counter.p, 0, sizeof(unsigned int)));
+  }
   return 0;
 }
 

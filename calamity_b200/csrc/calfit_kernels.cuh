@@ -895,6 +895,14 @@ struct GainsParams {
   int eval;             // 1: stand-alone gradient evaluation (no step in flight)
   PeerView peers;       // mode 2 with peers.n > 1: gradient = sum over ranks (rank order) of their published partials
   int xpar;             // parity of the step sequence number
+  // reduce-only modes, multi-GPU: the LAST CTA to finish also reduces the fused kernel's per-item partial sums into
+  // this rank's exchange buffer and publishes the step (saves two launches per iteration)
+  unsigned int* tail_counter;
+  const double* tail_partials;
+  int tail_npartials;
+  double* tail_scal;
+  unsigned int* tail_flag;
+  unsigned int tail_value;
 };
 
 // One CTA per (antenna, 64-channel block): 32 lanes along frequency (two adjacent channels each: z / y rows are read
@@ -986,23 +994,70 @@ __global__ void __launch_bounds__(GK_THREADS) gains_kernel(const GainsParams p) 
     }
     sh[eg][lane] = make_float4(acc_r.x, acc_r.y, acc_i.x, acc_i.y);
     __syncthreads();
-    if (eg != 0 || !f_ok) return;
-    float4 t = sh[0][lane];
+    const bool writer = eg == 0 && f_ok;
+    if (writer) {
+      float4 t = sh[0][lane];
 #pragma unroll
-    for (int g = 1; g < GK_EG; ++g) {  // fixed order
-      const float4 u = sh[g][lane];
-      t.x += u.x;
-      t.y += u.y;
-      t.z += u.z;
-      t.w += u.w;
+      for (int g = 1; g < GK_EG; ++g) {  // fixed order
+        const float4 u = sh[g][lane];
+        t.x += u.x;
+        t.y += u.y;
+        t.z += u.z;
+        t.w += u.w;
+      }
+      acc_r = make_float2(t.x, t.y);
+      acc_i = make_float2(t.z, t.w);
+      if (p.grad_r) {
+        *reinterpret_cast<float2*>(p.grad_r + o) = acc_r;
+        *reinterpret_cast<float2*>(p.grad_i + o) = acc_i;
+      }
     }
-    acc_r = make_float2(t.x, t.y);
-    acc_i = make_float2(t.z, t.w);
-    if (p.grad_r) {
-      *reinterpret_cast<float2*>(p.grad_r + o) = acc_r;
-      *reinterpret_cast<float2*>(p.grad_i + o) = acc_i;
+    if (p.mode == 1 || p.mode == 4) {
+      if (p.tail_counter) {  // whole CTA: last-block-done, then partial sums + publication by that block
+        __shared__ bool is_last;
+        __shared__ double red[3][GK_THREADS / 32];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(p.tail_counter, 1u) == gridDim.x * gridDim.y - 1u;
+        __syncthreads();
+        if (is_last) {
+          double a = 0.0, b = 0.0, c = 0.0;
+          for (int i = threadIdx.x; i < p.tail_npartials; i += GK_THREADS) {  // fixed order
+            a += p.tail_partials[(size_t)i * 4 + 0];
+            b += p.tail_partials[(size_t)i * 4 + 1];
+            c += p.tail_partials[(size_t)i * 4 + 2];
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            b += __shfl_xor_sync(0xffffffffu, b, off);
+            c += __shfl_xor_sync(0xffffffffu, c, off);
+          }
+          if (lane == 0) {
+            red[0][eg] = a;
+            red[1][eg] = b;
+            red[2][eg] = c;
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            a = b = c = 0.0;
+            for (int w = 0; w < GK_THREADS / 32; ++w) {
+              a += red[0][w];
+              b += red[1][w];
+              c += red[2][w];
+            }
+            p.tail_scal[0] = a;
+            p.tail_scal[1] = b;
+            p.tail_scal[2] = c;
+            *p.tail_counter = 0u;
+            __threadfence_system();
+            st_release_sys(p.tail_flag, p.tail_value);
+          }
+        }
+      }
+      return;
     }
-    if (p.mode == 1 || p.mode == 4) return;
+    if (!writer) return;
   } else {
     if (eg != 0 || !f_ok) return;
     if (p.peers.n > 1) {  // fused all-reduce: every rank's partial straight from its owner's memory, fixed order

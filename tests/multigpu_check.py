@@ -32,7 +32,7 @@ def main():
     prob = synth.make(workload, init_gain_scatter=0.02, coeff_error=0.05)
     full = prob.layout()
     shard = make_shard(full, rank, world)
-    log("shard groups", shard.g0, shard.g1)
+    log("shard groups", len(shard.groups), "of", full.ngroups)
     plan = FitPlan(shard.layout, device=local)
     if comm == "peer":  # NVLink peer-memory exchange fused into the update kernels
         comm_init_peer(plan, rank, world)

@@ -40,7 +40,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     prob = synth.make("test6", init_gain_scatter=0.05, coeff_error=0.1, flag_fraction=0.1)
     full = prob.layout()
-    shard = make_shard(full, rank, world)
+    shard = make_shard(full, rank, world, mode=os.environ.get("CALB2_TEST_SHARD_MODE", "cyclic"))
     t = _tensors(shard.layout, prob, shard)
     # chi^2 part and the regulariser sums of this rank's groups
     loss, dgr, dgi, dfr, dfi = R.loss_and_grads(t["g_r"], t["g_i"], t["fg_r"], t["fg_i"], t["data_r"], t["data_i"],
@@ -50,12 +50,17 @@ def _worker(rank, world, port, out):
     n = dgr.size
     if rank == 0:
         np.savez(out, dgr=buf[:n].numpy().reshape(dgr.shape), dgi=buf[n : 2 * n].numpy().reshape(dgi.shape),
-                 loss=buf[-1].item(), dfr0=shard.layout.flatten_coeffs(dfr), c0=shard.coef0, c1=shard.coef1)
+                 loss=buf[-1].item(), dfr0=shard.layout.flatten_coeffs(dfr), cidx=shard.coef_index)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_gradient_equals_unsharded(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("mode", ["cyclic", "contiguous"])
+def test_sharded_gradient_equals_unsharded(tmp_path, mode, monkeypatch):
+    monkeypatch.setenv("CALB2_TEST_SHARD_MODE", mode)
     out = str(tmp_path / "rank0.npz")
     port = _free_port()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
@@ -68,14 +73,14 @@ def test_sharded_gradient_equals_unsharded(tmp_path):
     assert abs(got["loss"] - float(loss)) < 1e-12 * abs(float(loss))
     assert np.allclose(got["dgr"], dgr, rtol=1e-10, atol=1e-14) and np.allclose(got["dgi"], dgi, rtol=1e-10, atol=1e-14)
     flat = full.flatten_coeffs(dfr).astype(np.float64)
-    assert np.allclose(got["dfr0"], flat[int(got["c0"]) : int(got["c1"])], rtol=1e-6)
+    assert np.allclose(got["dfr0"], flat[got["cidx"]], rtol=1e-6)
 
 
 def test_shards_tile_the_problem():
     prob = synth.make("hera37")
     full = prob.layout()
     for world in (2, 3, 8):
-        shards = [make_shard(full, r, world) for r in range(world)]
+        shards = [make_shard(full, r, world, mode="contiguous") for r in range(world)]
         assert shards[0].g0 == 0 and shards[-1].g1 == full.ngroups
         assert sum(s.layout.nbls for s in shards) == full.nbls
         assert sum(s.layout.ncoef for s in shards) == full.ncoef
@@ -83,3 +88,12 @@ def test_shards_tile_the_problem():
         assert np.array_equal(got, prob.data_r)
         loads = np.array([int(s.layout.group_ncomp.sum()) + 10 * s.layout.nbls for s in shards])
         assert loads.max() - loads.min() <= int(full.group_ncomp.max()) + 10
+        # cyclic: every group exactly once, loads within a few groups of each other, antenna degrees even
+        shards = [make_shard(full, r, world) for r in range(world)]
+        assert np.array_equal(np.sort(np.concatenate([s.groups for s in shards])), np.arange(full.ngroups))
+        assert np.array_equal(np.sort(np.concatenate([s.bl_index for s in shards])), np.arange(full.nbls))
+        assert np.array_equal(np.sort(np.concatenate([s.coef_index for s in shards])), np.arange(full.ncoef))
+        loads = np.array([int(s.layout.group_ncomp.sum()) + 10 * s.layout.nbls for s in shards])
+        assert loads.max() - loads.min() <= 0.05 * loads.mean() + int(full.group_ncomp.max()) + 10
+        deg = np.array([np.bincount(np.concatenate([s.layout.bl_ant0, s.layout.bl_ant1]), minlength=full.nants) for s in shards])
+        assert deg.max() <= 2 * np.ceil((full.nants - 1) / world) + 2  # contiguous ranges: up to nants - 1 on one rank
