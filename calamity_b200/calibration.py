@@ -149,40 +149,86 @@ def _resolve_baseline(uvdata, ants_map_inv, i, j, polarization, time):
     return int(rows[hit]), conj, pind
 
 
+def _rows_at_time(obj, time):
+    """{(ant1, ant2): row} of the baseline-time rows of a UVData / UVFlag-like object at `time`."""
+    rows = np.nonzero(np.isclose(np.asarray(obj.time_array), time, rtol=0.0, atol=1e-7))[0]
+    if hasattr(obj, "ant_1_array"):
+        a1, a2 = np.asarray(obj.ant_1_array)[rows], np.asarray(obj.ant_2_array)[rows]
+        return {(int(a), int(b)): int(r) for a, b, r in zip(a1.tolist(), a2.tolist(), rows.tolist())}
+    out = {}  # objects that only expose antpair2ind (UVFlag)
+    at_time = set(rows.tolist())
+    for ap in obj.get_antpairs():
+        for r in np.asarray(obj.antpair2ind(*ap)).tolist():
+            if r in at_time:
+                out[(int(ap[0]), int(ap[1]))] = int(r)
+    return out
+
+
+def _resolve_baselines(uvdata, ants_map_inv, bl_pairs, polarization, time):
+    """Vectorised form of the per-baseline lookups of calibration.py:260-272: for every antenna-index pair the row of
+    `uvdata` at `time`, whether the baseline is stored the other way round, and the polarization index to read.
+    A baseline counts as stored "forward" when its (ant1, ant2) ordering exists at ANY time (that is what
+    `_key2inds` looks at); a baseline absent at `time` raises IndexError, as upstream."""
+    stored = set((int(a), int(b)) for a, b in uvdata.get_antpairs())
+    at_time = _rows_at_time(uvdata, time)
+    rows = np.empty(len(bl_pairs), dtype=np.int64)
+    conj = np.zeros(len(bl_pairs), dtype=bool)
+    first_fwd = first_rev = None
+    for n, (i, j) in enumerate(bl_pairs):
+        ap = (int(ants_map_inv[i]), int(ants_map_inv[j]))
+        if ap in stored:
+            if first_fwd is None:
+                first_fwd = ap
+        elif ap[::-1] in stored:
+            conj[n] = True
+            ap = ap[::-1]
+            if first_rev is None:
+                first_rev = ap[::-1]
+        else:
+            raise KeyError(f"antenna pair {ap} not found in data")
+        if ap not in at_time:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # np.where(...)[0][0] upstream
+        rows[n] = at_time[ap]
+    pind_f = pind_r = 0
+    if first_fwd is not None:
+        pind_f = int(np.asarray(uvdata._key2inds(first_fwd + (polarization,))[2][0]).ravel()[0])
+    if first_rev is not None:
+        pind_r = int(np.asarray(uvdata._key2inds(first_rev + (polarization,))[2][1]).ravel()[0])
+    return rows, conj, np.where(conj, pind_r, pind_f)
+
+
 def _tensorize_data_flat(uvdata, bl_pairs, ants_map, polarization, time, data_scale_factor, weights,
                          nsamples_in_weights, dtype):
-    """Per-baseline rows [nbls, nfreqs] of scaled data and normalised weights in `bl_pairs` order."""
+    """Per-baseline rows [nbls, nfreqs] of scaled data and normalised weights in `bl_pairs` order (the arithmetic of
+    calibration.py:257-303, vectorised over baselines: the reference's Python loop is O(Nbls) per integration)."""
     inv = {v: k for k, v in ants_map.items()}
-    nb, nf = len(bl_pairs), uvdata.Nfreqs
-    d_r = np.zeros((nb, nf), dtype=dtype)
-    d_i = np.zeros((nb, nf), dtype=dtype)
-    w = np.zeros((nb, nf), dtype=dtype)
-    wpol = None
-    for n, (i, j) in enumerate(bl_pairs):
-        row, conj, pind = _resolve_baseline(uvdata, inv, i, j, polarization, time)
-        vis = uvdata.data_array[row, 0, :, pind] / data_scale_factor
-        if conj:
-            vis = np.conj(vis)
-        d_r[n] = vis.real.astype(dtype)
-        d_i[n] = vis.imag.astype(dtype)
-        unflagged = ~uvdata.flag_array[row, 0, :, pind]
-        if weights is None:
-            w[n] = unflagged
-        else:
-            ap = (inv[i], inv[j])
-            rows = weights.antpair2ind(*ap) if ap in weights.get_antpairs() else weights.antpair2ind(*ap[::-1])
-            rows = np.asarray(rows)
-            wrow = rows[np.where(np.isclose(weights.time_array[rows], time, atol=1e-7, rtol=0.0))[0][0]]
-            if wpol is None:
-                wpol = np.where(weights.polarization_array == _polstr2num(polarization, x_orientation=weights.x_orientation))[0][0]
-            w[n] = weights.weights_array[wrow, 0, :, wpol].astype(dtype) * unflagged
-        if nsamples_in_weights:
-            w[n] *= uvdata.nsample_array[row, 0, :, pind]
+    rows, conj, pind = _resolve_baselines(uvdata, inv, bl_pairs, polarization, time)
+    vis = uvdata.data_array[rows, 0, :, pind] / data_scale_factor  # fancy indexing: a copy, [nbls, nfreqs]
+    vis = np.where(conj[:, None], np.conj(vis), vis)
+    d_r = np.ascontiguousarray(vis.real, dtype=dtype)
+    d_i = np.ascontiguousarray(vis.imag, dtype=dtype)
+    unflagged = ~uvdata.flag_array[rows, 0, :, pind]
+    if weights is None:
+        w = unflagged.astype(dtype)
+    else:
+        wat = _rows_at_time(weights, time)
+        wrows = np.empty(len(bl_pairs), dtype=np.int64)
+        for n, (i, j) in enumerate(bl_pairs):
+            ap = (int(inv[i]), int(inv[j]))
+            if ap not in wat and ap[::-1] in wat:
+                ap = ap[::-1]
+            if ap not in wat:
+                raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+            wrows[n] = wat[ap]
+        wpol = np.where(weights.polarization_array == _polstr2num(polarization, x_orientation=weights.x_orientation))[0][0]
+        w = weights.weights_array[wrows, 0, :, wpol].astype(dtype) * unflagged
+    if nsamples_in_weights:
+        w = (w * uvdata.nsample_array[rows, 0, :, pind]).astype(dtype)
     wsum = 0.0
-    for n in range(nb):  # same accumulation order as the reference's running python-float sum
-        wsum += np.sum(w[n])
+    for s in np.sum(w, axis=1).tolist():  # same accumulation order as the reference's running python-float sum
+        wsum += s
     w = (w / wsum).astype(dtype)
-    return d_r, d_i, w
+    return d_r, d_i, np.ascontiguousarray(w)
 
 
 def tensorize_data(
@@ -384,19 +430,26 @@ def insert_model_into_uvdata_tensor(
 ):
     """Write cube cells (i, j) back into the rows of `uvdata` at `time` (conjugating baselines stored the other
     way round) times `scale_factor` -- calibration.py:741-795.  In place."""
-    stored = set(uvdata.get_antpairs())
+    stored = set((int(a), int(b)) for a, b in uvdata.get_antpairs())
     pnum = np.where(uvdata.polarization_array == _polstr2num(polarization, x_orientation=uvdata.x_orientation))[0][0]
+    at_time = _rows_at_time(uvdata, time)
+    rows, ii, jj, sign = [], [], [], []
     for red in red_grps:
         for ap in red:
-            i, j = ants_map[ap[0]], ants_map[ap[1]]
-            if ap in stored:
-                rows = np.asarray(uvdata.antpair2ind(ap))
-                vis = model_r[i, j] + 1j * model_i[i, j]
-            else:
-                rows = np.asarray(uvdata.antpair2ind(ap[::-1]))
-                vis = model_r[i, j] - 1j * model_i[i, j]
-            row = rows[np.where(np.isclose(time, uvdata.time_array[rows], atol=1e-7, rtol=0.0))[0][0]]
-            uvdata.data_array[row, 0, :, pnum] = vis * scale_factor
+            key = (int(ap[0]), int(ap[1]))
+            fwd = key in stored
+            if not fwd:
+                key = key[::-1]
+            if key not in at_time:
+                raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+            rows.append(at_time[key])
+            ii.append(ants_map[ap[0]])
+            jj.append(ants_map[ap[1]])
+            sign.append(1.0 if fwd else -1.0)
+    if rows:
+        ii, jj = np.asarray(ii), np.asarray(jj)
+        vis = np.asarray(model_r)[ii, jj] + 1j * np.asarray(sign)[:, None] * np.asarray(model_i)[ii, jj]
+        uvdata.data_array[np.asarray(rows), 0, :, pnum] = vis * scale_factor
 
 
 def insert_gains_into_uvcal(uvcal, time, polarization, gains_re, gains_im):
