@@ -393,8 +393,17 @@ static int ensure_vout(calb2_plan* pl) {
   return 0;
 }
 
-// host [n][nf] -> device [n][nfp] through the pinned staging buffer
+// host [n][nf] -> device [n][nfp].  Arrays whose padding columns are zero (data, weights, sky model: the buffers are
+// zero-initialised and nothing ever writes non-zero values into the padding) go with ONE pitched copy straight from the
+// caller's memory -- a true asynchronous DMA when that memory is pinned, the driver's own staged pipeline otherwise.
+// The gain tables (padding = 1) still take the staging buffer + pad kernel; they are small.
 static int upload_padded(calb2_plan* pl, const float* src, float* dst, size_t nrows, float fill) {
+  if (fill == 0.f) {
+    CU(cudaMemcpy2DAsync(dst, (size_t)pl->nfp * sizeof(float), src, (size_t)pl->nf * sizeof(float), (size_t)pl->nf * sizeof(float),
+                         nrows, cudaMemcpyHostToDevice, pl->stream));
+    CU(cudaStreamSynchronize(pl->stream));
+    return 0;
+  }
   const size_t rows_per = std::max<size_t>(1, pl->staging_floats / (size_t)pl->nf);
   for (size_t r0 = 0; r0 < nrows; r0 += rows_per) {
     const size_t n = std::min(rows_per, nrows - r0);
@@ -407,15 +416,9 @@ static int upload_padded(calb2_plan* pl, const float* src, float* dst, size_t nr
   return 0;
 }
 static int download_unpadded(calb2_plan* pl, const float* src, float* dst, size_t nrows) {
-  const size_t rows_per = std::max<size_t>(1, pl->staging_floats / (size_t)pl->nf);
-  for (size_t r0 = 0; r0 < nrows; r0 += rows_per) {
-    const size_t n = std::min(rows_per, nrows - r0);
-    unpad_rows_kernel<<<(unsigned)n, 128, 0, pl->stream>>>(src + r0 * pl->nfp, pl->staging.p, pl->nf, pl->nfp);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(pl->h_staging, pl->staging.p, n * pl->nf * sizeof(float), cudaMemcpyDeviceToHost, pl->stream));
-    CU(cudaStreamSynchronize(pl->stream));
-    memcpy(dst + r0 * pl->nf, pl->h_staging, n * pl->nf * sizeof(float));
-  }
+  CU(cudaMemcpy2DAsync(dst, (size_t)pl->nf * sizeof(float), src, (size_t)pl->nfp * sizeof(float), (size_t)pl->nf * sizeof(float), nrows,
+                       cudaMemcpyDeviceToHost, pl->stream));
+  CU(cudaStreamSynchronize(pl->stream));
   return 0;
 }
 
