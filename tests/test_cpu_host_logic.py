@@ -251,3 +251,62 @@ def test_unknown_optimizer_is_a_keyerror(native_built):
 
     with pytest.raises(KeyError):
         FitPlan.fit(None, optimizer="NotAnOptimizer")
+
+
+def test_tensorize_data_with_uvflag_weights_multitime():
+    """UVFlag weights (calibration.py:287-296) on a two-time data set: the weights row of the requested time is used,
+    multiplied by the unflagged mask, and everything is normalised to unit sum (300-303)."""
+    uvd = fx.line_array(ntimes=2)
+    rng = np.random.default_rng(5)
+    uvd.flag_array[:] = rng.random(uvd.flag_array.shape) < 0.2
+    weights = fx.unit_weights(uvd)
+    weights.weights_array[:] = rng.uniform(0.5, 2.0, weights.weights_array.shape)
+    gains = fx.cal_utils.blank_uvcal_from_uvdata(uvd)
+    ants_map = {ant: i for i, ant in enumerate(gains.ant_array)}
+    comps = {((ap,),): np.ones((uvd.Nfreqs, 2)) for ap in uvd.get_antpairs()}
+    _, corr = calibration.tensorize_fg_model_comps_dict(comps, ants_map, uvd.Nfreqs)
+    t1 = np.unique(uvd.time_array)[1]
+    d_r, d_i, w = calibration.tensorize_data(uvd, corr, ants_map, "xx", t1, weights=weights, dtype=np.float64)
+    want_w, want_d = [], []
+    for grp in corr[0]:
+        (i, j), = grp
+        rows = uvd.antpair2ind(int(gains.ant_array[i]), int(gains.ant_array[j]))
+        row = rows[np.isclose(uvd.time_array[rows], t1, rtol=0.0, atol=1e-7)][0]
+        wrow = weights.antpair2ind(int(gains.ant_array[i]), int(gains.ant_array[j]))
+        wrow = wrow[np.isclose(weights.time_array[wrow], t1, rtol=0.0, atol=1e-7)][0]
+        want_w.append(weights.weights_array[wrow, 0, :, 0] * ~uvd.flag_array[row, 0, :, 0])
+        want_d.append(uvd.data_array[row, 0, :, 0])
+    want_w = np.asarray(want_w)
+    want_w = want_w / want_w.sum()
+    assert np.allclose(w[0].numpy()[:, 0], want_w, rtol=1e-13)
+    assert np.array_equal(d_r[0].numpy()[:, 0], np.asarray(want_d).real)
+    assert np.array_equal(d_i[0].numpy()[:, 0], np.asarray(want_d).imag)
+
+
+def test_insert_model_into_uvdata_tensor_conjugates_and_times():
+    """calibration.py:741-795: cube cell (i, j) goes to the row of the requested time only, conjugated when the data
+    store the baseline the other way round, times scale_factor."""
+    uvd = fx.line_array(ntimes=2)
+    gains = fx.cal_utils.blank_uvcal_from_uvdata(uvd)
+    ants_map = {ant: i for i, ant in enumerate(gains.ant_array)}
+    n, nf = uvd.Nants_data, uvd.Nfreqs
+    rng = np.random.default_rng(9)
+    m_r, m_i = rng.standard_normal((n, n, nf)), rng.standard_normal((n, n, nf))
+    aps = uvd.get_antpairs()
+    red_grps = [[ap if k % 2 == 0 else ap[::-1]] for k, ap in enumerate(aps)]  # half of them asked for reversed
+    before = uvd.data_array.copy()
+    t1 = np.unique(uvd.time_array)[1]
+    calibration.insert_model_into_uvdata_tensor(uvd, t1, "xx", ants_map, red_grps, m_r, m_i, scale_factor=2.5)
+    for k, ap in enumerate(aps):
+        rows = uvd.antpair2ind(ap)
+        r0 = rows[np.isclose(uvd.time_array[rows], np.unique(uvd.time_array)[0], rtol=0.0, atol=1e-7)][0]
+        r1 = rows[np.isclose(uvd.time_array[rows], t1, rtol=0.0, atol=1e-7)][0]
+        assert np.array_equal(uvd.data_array[r0], before[r0])  # the other time is untouched
+        i, j = ants_map[ap[0]], ants_map[ap[1]]
+        if k % 2 == 0:
+            want = (m_r[i, j] + 1j * m_i[i, j]) * 2.5
+        else:  # asked as (j, i): stored the other way round -> conjugate of cell (j, i)
+            want = (m_r[j, i] - 1j * m_i[j, i]) * 2.5
+        assert np.allclose(uvd.data_array[r1, 0, :, 0], want, rtol=1e-15)
+    with pytest.raises(IndexError):
+        calibration.insert_model_into_uvdata_tensor(uvd, t1 + 7.0, "xx", ants_map, red_grps, m_r, m_i)
