@@ -203,10 +203,11 @@ def _tensorize_data_flat(uvdata, bl_pairs, ants_map, polarization, time, data_sc
     calibration.py:257-303, vectorised over baselines: the reference's Python loop is O(Nbls) per integration)."""
     inv = {v: k for k, v in ants_map.items()}
     rows, conj, pind = _resolve_baselines(uvdata, inv, bl_pairs, polarization, time)
+    if len(pind) and np.all(pind == pind[0]):
+        pind = int(pind[0])  # one polarization index for all baselines (always, for xx / yy): plain row gathers
     vis = uvdata.data_array[rows, 0, :, pind] / data_scale_factor  # fancy indexing: a copy, [nbls, nfreqs]
-    vis = np.where(conj[:, None], np.conj(vis), vis)
     d_r = np.ascontiguousarray(vis.real, dtype=dtype)
-    d_i = np.ascontiguousarray(vis.imag, dtype=dtype)
+    d_i = np.ascontiguousarray(np.where(conj[:, None], -vis.imag, vis.imag), dtype=dtype)
     unflagged = ~uvdata.flag_array[rows, 0, :, pind]
     if weights is None:
         w = unflagged.astype(dtype)
