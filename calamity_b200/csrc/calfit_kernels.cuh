@@ -352,8 +352,11 @@ struct HeavyCfg {
   static constexpr int OFF_A = 0;
   static constexpr int OFF_VPART = OFF_A + NBUF * TILE_FLOATS * 4;
   static constexpr int OFF_QBUF = OFF_VPART + NSEG * 2 * FT * 4;
+  // coefficients, thread-major: [warp][row group][RPT_PAD] float2, so a thread fetches the coefficients of two
+  // consecutive steps with one LDS.128 (half the coefficient traffic on the shared-memory port)
+  static constexpr int RPT_PAD = (RPT + 1) & ~1;
   static constexpr int OFF_CBUF = OFF_QBUF + SMAX * NQ * FT * 4;
-  static constexpr int OFF_STEPSLOT = OFF_CBUF + KMAX * 8;
+  static constexpr int OFF_STEPSLOT = OFF_CBUF + NWARP * G * RPT_PAD * 8;
   static constexpr int OFF_SLOTSTEP0 = OFF_STEPSLOT + ((NSTEP + 15) / 16) * 16;
   static constexpr int OFF_SLOTBL0 = OFF_SLOTSTEP0 + (SMAX + 1) * 4 + 12;
   static constexpr int OFF_RED = OFF_SLOTBL0 + (SMAX + 1) * 4 + 12;
@@ -418,13 +421,16 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
       reinterpret_cast<float4*>(Abuf + C::TILE_FLOATS + it.nrows * FT)[e] = zero4;
     }
   }
-  for (int r = tid; r < C::KMAX; r += C::NTHR) {
+  for (int e = tid; e < C::NWARP * G * C::RPT_PAD; e += C::NTHR) {
+    // e = (warp * G + row group) * RPT_PAD + step  <->  row = ((warp * RPT + step) * G + row group)
+    const int i = e % C::RPT_PAD, wu = e / C::RPT_PAD;
+    const int r = ((wu / G) * RPT + i) * G + (wu % G);
     float2 c = make_float2(0.f, 0.f);
-    if (r < it.nrows && QMODE != QM_INIT) {
+    if (i < RPT && r < it.nrows && QMODE != QM_INIT) {
       const int ci = p.row_coef[it.row0 + r];
       if (ci >= 0) c = make_float2(p.c_r[ci], p.c_i[ci]);
     }
-    cbuf[r] = c;
+    cbuf[e] = c;
   }
   for (int s = tid; s < nsteps; s += C::NTHR) step_slot[s] = p.row_slot[it.row0 + s * G];
   for (int s = tid; s <= it.nslots; s += C::NTHR) {
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
     mbar_wait(&mbar[buf], (j >> 1) & 1);
     CALB2_TICK(0)
     const float* Ab = Abuf + buf * C::TILE_FLOATS + row_off;
-    const float2* cb = cbuf + step_base * G + usub;
+    const float4* cb4 = reinterpret_cast<const float4*>(cbuf + (warp * G + usub) * C::RPT_PAD);  // two steps per load
 
     // ---------------- phase F: forward contraction, partial per (warp, slot) ----------------
     if (warp_active) {
@@ -541,11 +547,13 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
           *reinterpret_cast<float4*>(vpart + (seg * 2 + 1) * FT + fl * 4) = vi;
         }
       };
+      float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (chg == 0u) {  // all of this warp's rows belong to one slot: branch-free stream
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
           const float4 a = *reinterpret_cast<const float4*>(Ab + i * G * FT);
-          const float2 c = cb[i * G];
+          if ((i & 1) == 0) cc = cb4[i >> 1];
+          const float2 c = (i & 1) ? make_float2(cc.z, cc.w) : make_float2(cc.x, cc.y);
           axpy4(c.x, a, vr);
           axpy4(c.y, a, vi);
         }
@@ -561,7 +569,8 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
             ++cur;
           }
           const float4 a = *reinterpret_cast<const float4*>(Ab + i * G * FT);
-          const float2 c = cb[i * G];
+          if ((i & 1) == 0) cc = cb4[i >> 1];
+          const float2 c = (i & 1) ? make_float2(cc.z, cc.w) : make_float2(cc.x, cc.y);
           axpy4(c.x, a, vr);
           axpy4(c.y, a, vi);
         }
