@@ -445,7 +445,7 @@ static int all_reduce(calb2_plan* pl, void* buf, size_t count, int dtype) {
 #else
 #define CALB2_STAGE()
 #endif
-static constexpr int NSTAGE = 8;  // boundaries per step: start, heavy, partials, gains-reduce, all-reduce, finalize, gains, coeffs
+[[maybe_unused]] static constexpr int NSTAGE = 8;  // boundaries per step: start, heavy, partials, gains-reduce, all-reduce, finalize, gains, coeffs
 
 static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freeze, bool want_fuse, float* hist,
                         cudaEvent_t ev0, cudaEvent_t ev1, long long* launches) {
