@@ -328,9 +328,11 @@ def _profile_dump(profile_log_dir, payload):
 
 
 def _run_fit(plan, lay, g_r, g_i, fg_r, fg_i, use_min, tol, maxsteps, optimizer, freeze_model, verbose,
-             n_profile_steps, profile_log_dir, model_regularization, priors, dtype, opt_kwargs):
+             n_profile_steps, profile_log_dir, model_regularization, priors, dtype, opt_kwargs, graph_mode=False):
     """Shared tail of fit_gains_and_foregrounds / calibrate_and_model_tensor: run the loop on a loaded plan
-    and translate the results back to the reference's shapes."""
+    and translate the results back to the reference's shapes.  `graph_mode=True` (the reference's "pre-compile the
+    computational graph", calibration.py:670-679) forces CUDA-graph replay of the step loop; otherwise the library
+    decides (graphs for small, launch-bound problems)."""
     if optimizer not in OPTIMIZERS:
         raise KeyError(optimizer)  # calibration.py:571
     dtype = _fit_dtype(dtype)
@@ -343,7 +345,7 @@ def _run_fit(plan, lay, g_r, g_i, fg_r, fg_i, use_min, tol, maxsteps, optimizer,
     pr, pi = priors
     hist, res = plan.fit(optimizer=optimizer, maxsteps=maxsteps, tol=tol, use_min=use_min, freeze_model=freeze_model,
                          model_regularization=model_regularization, prior_r_sum=pr, prior_i_sum=pi,
-                         n_profile_steps=n_profile_steps, **opt_kwargs)
+                         n_profile_steps=n_profile_steps, use_graph=True if graph_mode else None, **opt_kwargs)
     if n_profile_steps > 0:
         _profile_dump(profile_log_dir, dict(res, n_profile_steps=n_profile_steps, note="CUDA-event timings of the step "
                                             "loop; the profiled steps are real optimizer steps, as in the reference"))
@@ -390,7 +392,8 @@ def fit_gains_and_foregrounds(
     Same contract as the reference: one unrecorded warm-up step, then up to `maxsteps` recorded steps whose
     PRE-update loss goes into fit_history['loss']; stop when two consecutive recorded losses differ by less
     than `tol`; `use_min` returns the post-update parameters of the step with the smallest recorded loss.
-    `graph_mode` / `graph_args_dict` select TensorFlow execution modes and have no effect here.
+    `graph_mode=True` replays the step loop as a CUDA graph (the analogue of the reference's tf.function mode);
+    `graph_args_dict` holds tf.function options and has no effect here.
     """
     echo(f"Using {str(dtype)} precision.")
     echo(f"{datetime.datetime.now()} Provided the following opt_kwargs")
@@ -410,7 +413,7 @@ def fit_gains_and_foregrounds(
             priors = plan.prior_sums(lay.flatten_data(sky_model_r), lay.flatten_data(sky_model_i))
         out_gr, out_gi, c_r, c_i, fit_history = _run_fit(
             plan, lay, g_r, g_i, fg_r, fg_i, use_min, tol, maxsteps, optimizer, freeze_model, verbose, n_profile_steps,
-            profile_log_dir, model_regularization, priors, dtype, opt_kwargs)
+            profile_log_dir, model_regularization, priors, dtype, opt_kwargs, graph_mode=graph_mode)
     if freeze_model:
         fg_r_opt, fg_i_opt = fg_r, fg_i  # calibration.py:730-732: handed back untouched
     else:
@@ -626,7 +629,7 @@ def calibrate_and_model_tensor(
                         priors = plan.prior_sums(s_r, s_i)
                     out = _run_fit(plan, lay, g_r, g_i, None, None, use_min, tol, maxsteps, optimizer, freeze_model,
                                    verbose, n_profile_steps, profile_log_dir, model_regularization, priors, dtype,
-                                   opt_kwargs)
+                                   opt_kwargs, graph_mode=graph_mode)
                     g_r, g_i, _, _, fit_history_p[time_index] = out
                     vis_r, vis_i = plan.get_model()
                     cube_r = np.zeros((lay.nants, lay.nants, lay.nfreqs))
