@@ -57,7 +57,12 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
-static constexpr int RPT_DEFAULT = 11;  // steps per warp: 11 -> 45 KB tiles, 2 CTAs/SM (7 -> 3 CTAs/SM was measured slower)
+// steps per warp: 11 -> 45 KB tiles, 2 CTAs/SM.  -DCALB2_RPT=7 -DCALB2_MINB=3 builds the 3 CTAs/SM experiment.
+#ifndef CALB2_RPT
+#define CALB2_RPT 11
+#define CALB2_MINB 2
+#endif
+static constexpr int RPT_DEFAULT = CALB2_RPT;
 static constexpr int SMAX = 8;
 
 // ---- NCCL through dlopen (the library has no link-time dependency on it) -------------------------
@@ -230,7 +235,7 @@ static int choose_fl(const calb2_plan_desc* d, int RPT, int NWARP, int* fl_out) 
 
 template <int FL, bool SUM, int QMODE>
 static cudaError_t launch_heavy_t(const HeavyParams& hp, int nitems, cudaStream_t s) {
-  constexpr int RPT = RPT_DEFAULT, MINB = 2;
+  constexpr int RPT = RPT_DEFAULT, MINB = CALB2_MINB;
   using C = HeavyCfg<FL, SUM, RPT>;
   static bool configured = false;
   if (!configured) {
