@@ -200,7 +200,8 @@ class FitPlan:
 
 
 def comm_init_peer(plan, rank, world):
-    """Set up the NVLink peer-memory exchange with torch.distributed (any backend) as the out-of-band channel."""
+    """Set up the NVLink peer-memory exchange with torch.distributed (any backend) as the out-of-band channel.
+    Synchronise the ranks (e.g. `dist.barrier()`) before closing the plans: peers read each other's buffers."""
     import torch
     import torch.distributed as dist
 

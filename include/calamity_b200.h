@@ -188,7 +188,9 @@ int calb2_comm_unique_id(void* nccl_unique_id_out, const char* nccl_lib);
  * (64-byte cudaIpcMemHandle_t), the caller gathers the handles of all ranks (rank order) and hands them to every
  * rank.  Per iteration a rank writes its partial sums / gain-gradient partial into its own buffer and raises a flag;
  * the finalize and gain-update kernels read all ranks' partials over NVLink and add them in rank order, so the
- * reduction is fused into the consumers, deterministic and bit-identical on all ranks.  One node, <= 16 ranks. */
+ * reduction is fused into the consumers, deterministic and bit-identical on all ranks.  One node, <= 16 ranks.
+ * Lifetime: the peers read a rank's buffer during their own last step, so a plan must not be destroyed before every
+ * rank has returned from its last calb2_fit (synchronise the ranks before calb2_plan_destroy). */
 int calb2_comm_peer_export(calb2_plan* plan, void* ipc_handle_out);
 int calb2_comm_peer_import(calb2_plan* plan, const void* ipc_handles, int32_t rank, int32_t nranks);
 

@@ -53,6 +53,8 @@ def main():
               prior_r_sum=pr, prior_i_sum=pi)
     hist, res = plan.fit(**kw)
     g_r, g_i = plan.get_gains()
+    torch.cuda.synchronize()
+    dist.barrier()  # peers read this rank's exchange buffer in their last step: nobody frees it before all are done
     plan.close()
     log("sharded fit done", hist[:2], hist[-1])
     ok = True
