@@ -9,8 +9,9 @@ A "step" is one optimizer iteration (forward model, chi^2, gradient, Adamax upda
 (time, polarisation) integration.  W warm-up steps are run untimed, then exactly K steps are timed with CUDA
 events on the library's stream, bracketed by a barrier + device synchronize, max over ranks.  Inputs are larger
 than L2 for hera128/hera350 (2.3 / 26 GB streamed per step vs 126 MB of L2), so no explicit L2 flush is needed.
-At N > 1 the baseline groups of the ONE integration are sharded across ranks ("strong" scaling) with a
-per-iteration NCCL all-reduce of the gain gradient and three scalars.
+At N > 1 the baseline groups of the ONE integration are sharded across ranks ("strong" scaling); per iteration the
+gain gradient and three scalars are exchanged through NVLink peer memory and reduced inside the update kernels
+(`--comm nccl`: NCCL all-reduce instead).
 """
 import argparse
 import json
