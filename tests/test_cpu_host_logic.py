@@ -310,3 +310,38 @@ def test_insert_model_into_uvdata_tensor_conjugates_and_times():
         assert np.allclose(uvd.data_array[r1, 0, :, 0], want, rtol=1e-15)
     with pytest.raises(IndexError):
         calibration.insert_model_into_uvdata_tensor(uvd, t1 + 7.0, "xx", ants_map, red_grps, m_r, m_i)
+
+
+def test_header_is_plain_c_and_links_from_c(native_built, tmp_path):
+    """The boundary is a C ABI: include/calamity_b200.h must compile as C99 (no C++ in the signatures) and a C program
+    must link against the shared library and call into it without a GPU (calb2_version)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+
+    from calamity_b200 import _native
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = ROOT
+    src = tmp_path / "use_cabi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "calamity_b200.h"\n'
+        "int main(void) {\n"
+        "  calb2_plan_desc d; calb2_fit_options o; calb2_fit_result r; calb2_plan_info info;\n"
+        "  memset(&d, 0, sizeof d); memset(&o, 0, sizeof o); memset(&r, 0, sizeof r); memset(&info, 0, sizeof info);\n"
+        "  o.optimizer = CALB2_OPT_ADAMAX; o.regularization = CALB2_REG_SUM; d.dtype = CALB2_F64;\n"
+                '  printf("%s %d %d %d %d %d\\n", calb2_version(), (int)sizeof(calb2_plan_desc), (int)sizeof(calb2_fit_result),\n'
+        "         (int)sizeof(calb2_plan_info), (int)sizeof(calb2_fit_options), calb2_plan_create(0, 0));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "use_cabi"
+    libdir = os.path.dirname(_native.lib_path())
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lcalamity_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert "sm_100a" in " ".join(out)
+    # the ctypes mirrors have the sizes the C compiler gives the structs; a null description is refused
+    sizes = [int(x) for x in out[-5:-1]]
+    assert sizes == [C.sizeof(_native.PlanDesc), C.sizeof(_native.FitResult), C.sizeof(_native.PlanInfo),
+                     C.sizeof(_native.FitOptions)], sizes
+    assert int(out[-1]) == -1
