@@ -345,3 +345,35 @@ def test_header_is_plain_c_and_links_from_c(native_built, tmp_path):
     assert sizes == [C.sizeof(_native.PlanDesc), C.sizeof(_native.FitResult), C.sizeof(_native.PlanInfo),
                      C.sizeof(_native.FitOptions)], sizes
     assert int(out[-1]) == -1
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under calamity_b200/ (the product path) may import, open or execute
+    anything under oracle/ -- and there is no CPU fallback to route to: the native loader raises when the library is
+    missing."""
+    import ast
+
+    pkg = os.path.join(ROOT, "calamity_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if not name.endswith(".py"):
+                continue
+            path = os.path.join(dirpath, name)
+            tree = ast.parse(open(path).read(), filename=path)
+            for node in ast.walk(tree):
+                mods = []
+                if isinstance(node, ast.Import):
+                    mods = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    mods = [node.module or ""]
+                assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), (path, mods)
+            assert "oracle/" not in open(path).read().replace("oracle/restatement.py for provenance", ""), path
+    from calamity_b200 import _native
+
+    saved, saved_lib = _native._LIB_PATH, _native._lib
+    try:
+        _native._LIB_PATH, _native._lib = os.path.join(pkg, "_lib", "does_not_exist.so"), None
+        with pytest.raises(_native.NativeError):
+            _native.load()
+    finally:
+        _native._LIB_PATH, _native._lib = saved, saved_lib
