@@ -1,6 +1,7 @@
 // Device code of the B200-native gain-and-foreground fit (sm_100a).
 //
-// One optimizer iteration of calibration.py:663-668 is four launches on one stream:
+// One optimizer iteration of calibration.py:663-668 is four launches (the coefficient update is forked onto a second
+// stream next to the gain update; on several GPUs the gradient exchange goes through peer memory inside these kernels):
 //   heavy_kernel   streams the ragged foreground basis ONCE (cp.async.bulk -> shared memory, mbarrier
 //                  double buffering) and, per staged [rows x FT channels] tile, does the forward
 //                  contraction v = sum_k c_k A_k (calibration.py:1587-1590), the gain application,
@@ -9,8 +10,9 @@
 //   finalize_kernel reduces the per-CTA partial sums in a fixed order (deterministic), forms the loss
 //                  (1652-1656), records it, runs the use_min / tol logic of 699-717 on the device.
 //   gains_kernel   deterministic per-(antenna, channel) reduction of the gain gradient over the
-//                  baselines touching the antenna (CSR order, no atomics) + optimizer step on the gains.
+//                  baselines touching the antenna (CSR order, 8 entry groups, no atomics) + optimizer step on the gains.
 //   coeffs_kernel  optimizer step on the foreground coefficients (combines the regulariser terms).
+// float64 plans and groups too large for the staged tile use the kernels of calfit_generic.cuh instead.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
