@@ -33,6 +33,12 @@ FIT_CASES = {
                                       n_profile_steps=2, model_regularization="sum", profile_log_dir="/tmp/calb2_shim_prof"),
     "adamax_freeze": dict(optimizer="Adamax", maxsteps=40, tol=0.0, learning_rate=1e-2, freeze_model=True),
     "adamax_tol": dict(optimizer="Adamax", maxsteps=500, tol=2e-6, learning_rate=1e-2),
+    # the other entries of the reference's OPTIMIZERS table (calibration.py:17-27), hyper-parameters through **opt_kwargs
+    "sgd_momentum": dict(optimizer="SGD", maxsteps=30, tol=0.0, learning_rate=2e-3, momentum=0.9, nesterov=True),
+    "rmsprop": dict(optimizer="RMSprop", maxsteps=30, tol=0.0, learning_rate=1e-3, momentum=0.5),
+    "adagrad_sum": dict(optimizer="Adagrad", maxsteps=30, tol=0.0, learning_rate=1e-2, model_regularization="sum"),
+    "adadelta": dict(optimizer="Adadelta", maxsteps=30, tol=0.0, learning_rate=1.0),
+    "nadam": dict(optimizer="Nadam", maxsteps=30, tol=0.0, learning_rate=1e-2),
 }
 
 

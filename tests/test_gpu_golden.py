@@ -4,6 +4,8 @@ import os
 import numpy as np
 import pytest
 
+from oracle import restatement as R
+
 from calamity_b200 import calibration
 from tests import fixtures_uv as fx
 from tests import golden_inputs as gi
@@ -59,11 +61,24 @@ def test_g3_cuda_fit_trajectories(native_built, name):
     assert len(hist) == len(want)
     err = np.abs(hist.astype(np.float64) - want) / want
     print(f"\n{name}: max rel loss deviation from the reference-code float32 run: {err.max():.2e}")
-    if kw["learning_rate"] < 0.1:
-        assert err.max() < 1e-4  # two float32 evaluations of the same trajectory (both ~1e-6 from float64)
-        assert rel_err(g_r, GOLD[f"g3_{name}_g_r"]) < 1e-4 and rel_err(g_i, GOLD[f"g3_{name}_g_i"]) < 1e-4
-        assert rel_err(c_r, lay.flatten_coeffs([GOLD[f"g3_{name}_fg_r"]])) < 1e-4
-        assert rel_err(c_i, lay.flatten_coeffs([GOLD[f"g3_{name}_fg_i"]])) < 1e-4
+    if not (kw["learning_rate"] >= 0.1 and kw.get("use_min")):
+        # Two float32 evaluations of the same trajectory are compared: the bound on the parameters is 1e-4, or -- for
+        # rules that amplify rounding noise (division by sqrt(mean g^2); Nadam's fast convergence into the flat
+        # directions of the gains) -- eight times the distance of the reference-code float32 run itself from the float64
+        # restatement of the same trajectory, whichever is larger.
+        t64 = gi.reference_problem(np.float64)
+        kw64 = dict(gi.FIT_CASES[name])
+        kw64.pop("profile_log_dir", None)
+        o64 = R.fit(t64["g_r"], t64["g_i"], t64["fg_r"], t64["fg_i"], t64["data_r"], t64["data_i"], t64["wgts"], t64["fg_comps"],
+                    t64["corr_inds"], sky_model_r=t64["data_r"], sky_model_i=t64["data_i"], **kw64)
+        spread = max(rel_err(o64[0], GOLD[f"g3_{name}_g_r"]), rel_err(o64[1], GOLD[f"g3_{name}_g_i"]),
+                     rel_err(o64[2][0], GOLD[f"g3_{name}_fg_r"]), rel_err(o64[3][0], GOLD[f"g3_{name}_fg_i"]))
+        ptol = max(1e-4, 8.0 * spread)
+        errs = (rel_err(g_r, GOLD[f"g3_{name}_g_r"]), rel_err(g_i, GOLD[f"g3_{name}_g_i"]),
+                rel_err(c_r, lay.flatten_coeffs([GOLD[f"g3_{name}_fg_r"]])), rel_err(c_i, lay.flatten_coeffs([GOLD[f"g3_{name}_fg_i"]])))
+        print(f"{name}: parameter deviations {errs}, bound {ptol:.2e} (reference-code run vs float64: {spread:.2e})")
+        assert err.max() < 1e-4  # both ~1e-6 from float64
+        assert max(errs) < ptol, (errs, ptol)
     else:  # lr = 0.2 overshoots on purpose (use_min): chaotic amplification of rounding, compare loosely
         assert np.allclose(hist[:5], want[:5], rtol=1e-3)
         assert abs(float(res["final_loss"]) - float(hist.min())) <= 1e-7 * float(hist.min())
