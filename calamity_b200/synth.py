@@ -105,6 +105,28 @@ class SyntheticProblem:
         self.c0_r = np.ascontiguousarray(c0.real, dtype=np.float32)
         self.c0_i = np.ascontiguousarray(c0.imag, dtype=np.float32)
 
+    def select_baselines(self, sel):
+        """The same antennas, gains and realisation restricted to baselines `sel` (indices in canonical order):
+        a cheap way to get benchmark-shaped groups (350 antennas, 1024 channels, the longest baselines' 204-vector
+        bases) at a size a CPU oracle can follow.  Weights are renormalised to sum 1 (calibration.py:300-303)."""
+        import copy
+
+        sel = np.asarray(sel, dtype=np.int64)
+        sub = copy.copy(self)
+        keys = list(self.comps_dict.keys())
+        sub.comps_dict = {keys[b]: self.comps_dict[keys[b]] for b in sel}
+        sub.ant0, sub.ant1, sub.ncomp = self.ant0[sel], self.ant1[sel], self.ncomp[sel]
+        sub.nbls = len(sel)
+        sub.coef0 = np.concatenate([[0], np.cumsum(sub.ncomp)]).astype(np.int64)
+        cidx = (np.concatenate([np.arange(self.coef0[b], self.coef0[b + 1]) for b in sel]) if len(sel)
+                else np.zeros(0, np.int64))
+        sub.c_true, sub.c0_r, sub.c0_i = self.c_true[cidx], self.c0_r[cidx], self.c0_i[cidx]
+        sub.vis_true, sub.flags = self.vis_true[sel], self.flags[sel]
+        sub.data_r, sub.data_i = self.data_r[sel], self.data_i[sel]
+        w = self.wgts[sel].astype(np.float64)
+        sub.wgts = np.ascontiguousarray(w / w.sum(), dtype=np.float32)
+        return sub
+
     def layout(self):
         from .layout import RaggedLayout
 

@@ -1,0 +1,125 @@
+"""GPU parity at the shapes the bench times (BASELINE.json configs 3-5): HERA-128 and HERA-350 geometry at 1024
+channels -- groups of up to 204 basis vectors that span several warps of a staged item, 8-slot items, 32-channel
+tiles -- and a config-5-shaped mixed dict (joint groups of 11 redundant sub-groups, ~470 baselines, 300 / 400
+vectors).  The yardstick is the float64 ragged restatement (oracle/ragged.py, pinned to the dense restatement on CPU).
+Tolerances are BASELINE.json's: loss 1e-5, gradients 1e-4 (of the largest entry), parameters 1e-4 after 60 steps.
+"""
+import numpy as np
+import pytest
+
+from oracle.ragged import RaggedProblem
+from tests.helpers import flat_from_synth, long_baseline_subset, mixed_problem, rel_err, small_problem
+
+pytestmark = pytest.mark.gpu
+F = np.float64
+
+
+def _plan(p, **kw):
+    from calamity_b200.fitter import FitPlan
+
+    plan = FitPlan(p.lay, device=0, **kw)
+    plan.set_integration(p.data_r, p.data_i, p.wgts)
+    plan.set_gains(p.g0_r, p.g0_i)
+    plan.set_coeffs(p.c0_r, p.c0_i)
+    return plan
+
+
+def _args64(p):
+    return [np.asarray(x, dtype=F) for x in (p.g0_r, p.g0_i, p.c0_r, p.c0_i, p.data_r, p.data_i, p.wgts)]
+
+
+def _priors(p):
+    return (float(np.sum(p.data_r.astype(F) * p.wgts)) * 0.9, float(np.sum(p.data_i.astype(F) * p.wgts)) * 1.1)
+
+
+def _check_loss_and_grads(p, plan_kw=None, regs=(None, "sum")):
+    rp = RaggedProblem(p.lay)
+    pr, pi = _priors(p)
+    plan = _plan(p, **(plan_kw or {}))
+    info = dict(plan.info)
+    try:
+        for reg in regs:
+            ol, ogr, ogi, ocr, oci = rp.loss_and_grads(*_args64(p), regularization=reg, prior_r_sum=F(pr), prior_i_sum=F(pi))
+            loss, dgr, dgi, dcr, dci = plan.loss_and_grads(model_regularization=reg, prior_r_sum=pr, prior_i_sum=pi)
+            errs = (abs(float(loss) - float(ol)) / abs(float(ol)), rel_err(dgr, ogr), rel_err(dgi, ogi), rel_err(dcr, ocr),
+                    rel_err(dci, oci))
+            print(f"\n  reg={reg}: loss {float(loss):.6e} rel err {errs[0]:.1e}; grad rel errs g {errs[1]:.1e} {errs[2]:.1e} "
+                  f"c {errs[3]:.1e} {errs[4]:.1e}; tile {info['tile_freqs']}, items {info['nitems']}")
+            assert errs[0] <= 1e-5
+            assert max(errs[1:]) < 1e-4
+    finally:
+        plan.close()
+    return info
+
+
+def _check_trajectory(p, reg, nsteps=60, plan_kw=None):
+    rp = RaggedProblem(p.lay)
+    pr = float(np.sum(p.data_r.astype(F) * p.wgts))
+    pi = float(np.sum(p.data_i.astype(F) * p.wgts))
+    kw = dict(optimizer="Adamax", maxsteps=nsteps, tol=0.0, learning_rate=1e-2, model_regularization=reg)
+    o = rp.fit(p.g0_r, p.g0_i, p.c0_r, p.c0_i, p.data_r, p.data_i, p.wgts, prior_r_sum=F(np.float32(pr)),
+               prior_i_sum=F(np.float32(pi)), **kw)
+    plan = _plan(p, **(plan_kw or {}))
+    try:
+        hist, res = plan.fit(prior_r_sum=pr, prior_i_sum=pi, **kw)
+        g_r, g_i = plan.get_gains()
+        c_r, c_i = plan.get_coeffs()
+    finally:
+        plan.close()
+    ref = np.asarray(o[4]["loss"], dtype=F)
+    err = np.abs(hist.astype(F) - ref) / ref
+    perr = (rel_err(g_r, o[0]), rel_err(g_i, o[1]), rel_err(c_r, o[2]), rel_err(c_i, o[3]))
+    print(f"\n  {nsteps}-step Adamax reg={reg}: loss {ref[0]:.4e} -> {ref[-1]:.4e}, max rel loss err {err.max():.1e}, "
+          f"gain err {perr[0]:.1e} {perr[1]:.1e}, coeff err {perr[2]:.1e} {perr[3]:.1e}")
+    assert res["nsteps_recorded"] == nsteps
+    assert err.max() < 1e-5
+    assert max(perr) < 1e-4
+
+
+@pytest.fixture(scope="module")
+def hera128():
+    return small_problem("hera128", init_gain_scatter=0.02, coeff_error=0.05)
+
+
+@pytest.fixture(scope="module")
+def hera350():
+    return small_problem("hera350", init_gain_scatter=0.02, coeff_error=0.05)
+
+
+def test_hera128_full_loss_and_gradient(native_built, hera128):
+    """All 8128 baselines x 1024 channels, both regularisations."""
+    info = _check_loss_and_grads(flat_from_synth(hera128))
+    assert info["nbls_total"] == 8128
+
+
+@pytest.mark.parametrize("reg", [None, "sum"])
+def test_hera128_long_baseline_trajectory(native_built, hera128, reg):
+    sub = hera128.select_baselines(long_baseline_subset(hera128, every=6, n_long=300))
+    _check_trajectory(flat_from_synth(sub), reg)
+
+
+def test_hera350_full_loss_and_gradient(native_built, hera350):
+    """The bench workload itself: 61 075 baselines x 1024 channels (26 GB of basis on the streaming path)."""
+    info = _check_loss_and_grads(flat_from_synth(hera350), regs=(None,))
+    assert info["nbls_total"] == 61075
+
+
+@pytest.mark.parametrize("reg", [None, "sum"])
+def test_hera350_long_baseline_subset(native_built, hera350, reg):
+    """350 antennas, the 400 longest baselines (ncomp up to 204: five warps per slot, one or two slots per item) and every
+    40th of the rest: loss / gradient and a 60-step trajectory."""
+    sub = hera350.select_baselines(long_baseline_subset(hera350, every=40, n_long=400))
+    assert int(sub.ncomp.max()) == int(hera350.ncomp.max())
+    p = flat_from_synth(sub)
+    _check_loss_and_grads(p, regs=(reg,))
+    _check_trajectory(p, reg)
+
+
+@pytest.mark.parametrize("ncomp", [300, 400])
+def test_config5_mixed_joint_groups(native_built, ncomp):
+    """One joint group of 11 ragged redundant sub-groups (~470 baselines) with 300 vectors (one slot per staged item at 32
+    channels per tile) or 400 vectors (forces 16-channel tiles), plus 300 per-baseline DPSS groups."""
+    p = mixed_problem(nants=128, nfreqs=1024, seed=7 + ncomp, n_dpss_bls=300, joint=((11, 43, ncomp),))
+    info = _check_loss_and_grads(p)
+    assert info["tile_freqs"] == (32 if ncomp <= 352 else 16)
+    _check_trajectory(p, "sum")
