@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--fuse", type=int, default=0)
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gain-gradient exchange fused into the update kernel over NVLink peer memory, or NCCL")
+    ap.add_argument("--shared-basis", type=int, default=0, choices=[-1, 0, 1],
+                    help="0: groups that share a basis block take the shared-basis kernel (default); -1: stream a private "
+                         "copy per group (round-1 path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     # CPU arm: ~10-20 s of host work -- 2048 of the 61 075 baselines (dense padded basis 1.7 GB), 20 steps
     ap.add_argument("--cpu-sample-bls", type=int, default=2048)
@@ -239,7 +242,7 @@ def main():
     full = prob.layout()
     sizes = full.sizes()
     shard = make_shard(full, rank, world)
-    plan = FitPlan(shard.layout, device=local_rank, tile_freqs=args.tile)
+    plan = FitPlan(shard.layout, device=local_rank, tile_freqs=args.tile, shared_basis=args.shared_basis)
     if world > 1 and args.comm == "peer":
         comm_init_peer(plan, rank, world)
     elif world > 1:

@@ -29,6 +29,8 @@ class PlanDesc(C.Structure):
         ("bl_ant1", C.POINTER(C.c_int32)),
         ("tile_freqs", C.c_int32),
         ("dtype", C.c_int32),
+        ("group_class", C.POINTER(C.c_int32)),
+        ("shared_basis", C.c_int32),
     ]
 
 
@@ -86,6 +88,12 @@ class PlanInfo(C.Structure):
         ("device_bytes", C.c_int64),
         ("generic", C.c_int32),
         ("dtype", C.c_int32),
+        ("n_classes", C.c_int64),
+        ("n_class_slots", C.c_int64),
+        ("n_class_ctas", C.c_int64),
+        ("n_a_class", C.c_int64),
+        ("n_a_class_nz", C.c_int64),
+        ("class_fma", C.c_int64),
     ]
 
 

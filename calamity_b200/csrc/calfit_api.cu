@@ -15,6 +15,7 @@
 
 #include "../../include/calamity_b200.h"
 #include "calfit_kernels.cuh"
+#include "calfit_shared.cuh"
 #include "calfit_setup.cuh"
 #include "calfit_generic.cuh"
 
@@ -120,6 +121,23 @@ struct calb2_plan {
   std::vector<int> grp_ncomp, grp_nslots, grp_slot0, grp_coef0, slot_nbls, slot_grp, slot_row0, slot_bl0, slot_item,
       bl_ant0, bl_ant1, bl_slot;
   std::vector<ItemDesc> items;
+  // shared-basis path (calfit_shared.cuh): single-slot groups whose basis block is shared by enough other groups.
+  // Slots are numbered INTERNALLY: streaming-path slots first (canonical order), then the class slots, class by class.
+  struct ClsInfo {
+    long long a_off;  // float offset of the class's [ntiles][kp][32] swizzled block in A
+    int kp, ncomp;
+    int nmembers;
+    bool uploaded;
+  };
+  std::vector<ClsInfo> classes;
+  std::vector<int> grp_cls;           // dense class index of the group, or -1: streaming path
+  std::vector<MTileDesc> mtiles[2];   // [0]: 64 groups per CTA (NQ = 2), [1]: 32 groups per CTA (NQ = 4, 'sum')
+  DevBuf<MTileDesc> d_mtiles[2];
+  DevBuf<ClassSlot> d_cslots;
+  DevBuf<int> d_cs_slot, d_slot_nb;
+  long long nslots_heavy = 0, nslots_class = 0, a_class_floats = 0;
+  int ntiles_c = 0;
+  bool heavy_single_bl = true, cls_single_bl = true;
   // device
   DevBuf<float> A, d_r, d_i, w, g_r[2], g_i[2], gm_r, gu_r, gm_i, gu_i, gsnap_r, gsnap_i, ggrad_r, ggrad_i;
   DevBuf<float> c_r, c_i, cm_r, cu_r, cm_i, cu_i, csnap_r, csnap_i, cgrad_r, cgrad_i, dcpart, hist, scratch_f;
@@ -256,14 +274,65 @@ static cudaError_t launch_heavy_f(bool sum, int qmode, const HeavyParams& hp, in
   return sum ? launch_heavy_t<FL, true, QM_GENERAL>(hp, nitems, s) : launch_heavy_t<FL, false, QM_GENERAL>(hp, nitems, s);
 }
 
-static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
-  const int qmode = hp.init_mode ? QM_INIT : (pl->all_single_bl ? QM_SINGLE : QM_GENERAL);
-  switch (pl->FL) {
-    case 16: return launch_heavy_f<16>(sum, qmode, hp, nitems, s);
-    case 8: return launch_heavy_f<8>(sum, qmode, hp, nitems, s);
-    default: return launch_heavy_f<4>(sum, qmode, hp, nitems, s);
+template <int MS, int NQ, bool SINGLE>
+static cudaError_t launch_shared_t(const SharedParams& sp, int ntiles, cudaStream_t s) {
+  using C = SharedCfg<MS, NQ>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(shared_kernel<MS, NQ, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
   }
+  shared_kernel<MS, NQ, SINGLE><<<ntiles, C::NTHR, C::SMEM_BYTES, s>>>(sp);
+  return cudaGetLastError();
 }
+
+// The basis pass of one iteration: the streaming kernel over the items (groups with a private basis) and the
+// shared-basis kernel over the class tiles; both write z / dcpart / partials for their own baselines and rows.
+static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
+  if (nitems > 0) {
+    const int qmode = hp.init_mode ? QM_INIT : (pl->heavy_single_bl ? QM_SINGLE : QM_GENERAL);
+    cudaError_t e;
+    switch (pl->FL) {
+      case 16: e = launch_heavy_f<16>(sum, qmode, hp, nitems, s); break;
+      case 8: e = launch_heavy_f<8>(sum, qmode, hp, nitems, s); break;
+      default: e = launch_heavy_f<4>(sum, qmode, hp, nitems, s); break;
+    }
+    if (e != cudaSuccess) return e;
+  }
+  const int v = sum ? 1 : 0;
+  const int nmt = (int)pl->mtiles[v].size();
+  if (nmt == 0) return cudaSuccess;
+  SharedParams sp{};
+  sp.A = hp.A;
+  sp.tiles = pl->d_mtiles[v].p;
+  sp.cslots = pl->d_cslots.p;
+  sp.cs_slot = pl->d_cs_slot.p;
+  sp.bl_ant0 = hp.bl_ant0;
+  sp.bl_ant1 = hp.bl_ant1;
+  sp.d_r = hp.d_r;
+  sp.d_i = hp.d_i;
+  sp.w = hp.w;
+  for (int b = 0; b < 2; ++b) {
+    sp.g_r[b] = hp.g_r[b];
+    sp.g_i[b] = hp.g_i[b];
+  }
+  sp.c_r = hp.c_r;
+  sp.c_i = hp.c_i;
+  sp.z = hp.z;
+  sp.y = hp.y;
+  sp.dcpart = hp.dcpart;
+  sp.vout = hp.vout;
+  sp.partials = hp.partials + (size_t)nitems * 4;
+  sp.st = hp.st;
+  sp.nfp = hp.nfp;
+  sp.ntiles = pl->ntiles_c;
+  sp.store_v = hp.store_v;
+  sp.init_mode = hp.init_mode;
+  if (sum) return pl->cls_single_bl ? launch_shared_t<32, 4, true>(sp, nmt, s) : launch_shared_t<32, 4, false>(sp, nmt, s);
+  return pl->cls_single_bl ? launch_shared_t<64, 2, true>(sp, nmt, s) : launch_shared_t<64, 2, false>(sp, nmt, s);
+}
+static int n_partials(const calb2_plan* pl, bool sum) { return (int)(pl->items.size() + pl->mtiles[sum ? 1 : 0].size()); }
 
 static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, int store_v, int init_mode) {
   HeavyParams hp{};
@@ -273,6 +342,7 @@ static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, in
   hp.row_coef = pl->row_coef.p;
   hp.slot_row0 = pl->d_slot_row0.p;
   hp.slot_bl0 = pl->d_slot_bl0.p;
+  hp.slot_nb = pl->d_slot_nb.p;
   hp.bl_ant0 = pl->d_bl_ant0.p;
   hp.bl_ant1 = pl->d_bl_ant1.p;
   hp.d_r = pl->d_r.p;
@@ -455,8 +525,9 @@ static int all_reduce(calb2_plan* pl, void* buf, size_t count, int dtype) {
 static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freeze, bool want_fuse, float* hist,
                         cudaEvent_t ev0, cudaEvent_t ev1, long long* launches) {
   // coefficients can take their optimizer step in the heavy kernel's tail when nothing couples the groups
-  const bool fuse = want_fuse && !sum && !freeze && pl->all_single_slot && k.optimizer <= CALB2_OPT_SGD && k.momentum == 0.f;
-  int npartials = (int)pl->items.size();
+  const bool fuse = want_fuse && !sum && !freeze && pl->all_single_slot && pl->mtiles[0].empty() &&
+                    k.optimizer <= CALB2_OPT_SGD && k.momentum == 0.f;
+  int npartials = n_partials(pl, sum);
   const double* partials = pl->partials.p;
   if (ev0) CU(cudaEventRecord(ev0, pl->stream));
   CALB2_STAGE()
@@ -721,14 +792,64 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   if (!d || !out) return fail(CALB2_ERR_ARG, "null argument");
   if (d->nants <= 0 || d->nfreqs <= 0 || d->ngroups <= 0) return fail(CALB2_ERR_ARG, "empty problem");
   const int rpt = RPT_DEFAULT, nwarp = 8;
-  int fl = 0;
   if (d->dtype != CALB2_F32 && d->dtype != CALB2_F64) return fail(CALB2_ERR_ARG, "dtype must be CALB2_F32 or CALB2_F64");
+  for (int g = 0; g < d->ngroups; ++g)
+    if (d->group_ncomp[g] < 0 || d->group_nslots[g] <= 0) return fail(CALB2_ERR_ARG, "group %d: bad ncomp/nslots", g);
   // float64, or a group with more basis vectors than the fused kernel stages: the generic unfused path
   bool generic = d->dtype == CALB2_F64 || (getenv("CALB2_GENERIC") && atoi(getenv("CALB2_GENERIC")) != 0);
-  if (int r = choose_fl(d, rpt, nwarp, &fl)) {
-    if (r != CALB2_ERR_UNSUPPORTED || d->tile_freqs) return r;
-    generic = true;
-    fl = 8;
+
+  // ---- shared-basis classes: single-slot groups whose basis block is shared by at least `min_members` groups ----
+  std::vector<int> grp_cls(d->ngroups, -1);
+  std::vector<std::vector<int>> cls_members;
+  int shared_mode = d->shared_basis;
+  if (getenv("CALB2_SHARED_BASIS")) shared_mode = atoi(getenv("CALB2_SHARED_BASIS"));
+  if (d->group_class && shared_mode >= 0 && !generic) {
+    int min_members = shared_mode >= 1 ? 1 : 4;
+    if (getenv("CALB2_CLS_MIN")) min_members = std::max(1, atoi(getenv("CALB2_CLS_MIN")));
+    std::unordered_map<int, int> index_of;  // class id -> position in `cands` (first-appearance order: deterministic)
+    std::vector<std::vector<int>> cands;
+    for (int g = 0; g < d->ngroups; ++g) {
+      const int id = d->group_class[g];
+      if (id < 0 || d->group_nslots[g] != 1 || d->group_ncomp[g] < 1 || d->group_ncomp[g] > SharedCfg<64, 2>::KROWS) continue;
+      auto it = index_of.find(id);
+      if (it == index_of.end()) {
+        it = index_of.emplace(id, (int)cands.size()).first;
+        cands.emplace_back();
+      }
+      cands[it->second].push_back(g);
+    }
+    for (auto& mem : cands) {
+      if ((int)mem.size() < min_members) continue;
+      for (int g : mem)
+        if (d->group_ncomp[g] != d->group_ncomp[mem[0]])
+          return fail(CALB2_ERR_ARG, "groups %d and %d share a basis class but have %d and %d vectors", mem[0], g,
+                      d->group_ncomp[mem[0]], d->group_ncomp[g]);
+      for (int g : mem) grp_cls[g] = (int)cls_members.size();
+      cls_members.push_back(mem);
+    }
+  }
+  // tile width of the streaming path, from the groups that stay on it
+  int fl = 8;
+  {
+    std::vector<int32_t> h_ncomp, h_nslots;
+    for (int g = 0; g < d->ngroups; ++g)
+      if (grp_cls[g] < 0) {
+        h_ncomp.push_back(d->group_ncomp[g]);
+        h_nslots.push_back(d->group_nslots[g]);
+      }
+    if (!h_ncomp.empty()) {
+      calb2_plan_desc hd = *d;
+      hd.ngroups = (int32_t)h_ncomp.size();
+      hd.group_ncomp = h_ncomp.data();
+      hd.group_nslots = h_nslots.data();
+      if (int r = choose_fl(&hd, rpt, nwarp, &fl)) {
+        if (r != CALB2_ERR_UNSUPPORTED || d->tile_freqs) return r;
+        generic = true;  // single GPU, no classes
+        fl = 8;
+        std::fill(grp_cls.begin(), grp_cls.end(), -1);
+        cls_members.clear();
+      }
+    }
   }
   CU(cudaSetDevice(d->device));
   calb2_plan* pl = new calb2_plan();
@@ -743,42 +864,72 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   pl->RPT = rpt;
   pl->NW = nwarp;
   pl->KMAX = nwarp * rpt * pl->G;
-  pl->ntiles = (pl->nf + pl->FT - 1) / pl->FT;
-  pl->nfp = pl->ntiles * pl->FT;
+  {
+    const int quantum = cls_members.empty() ? pl->FT : std::max(pl->FT, SharedCfg<64, 2>::FT);
+    pl->nfp = ((pl->nf + quantum - 1) / quantum) * quantum;
+  }
+  pl->ntiles = pl->nfp / pl->FT;
+  pl->ntiles_c = pl->nfp / SharedCfg<64, 2>::FT;
+  pl->grp_cls = grp_cls;
   const int G = pl->G;
 
-  // ---- flatten groups -> slots -> baselines ----
+  // ---- flatten groups -> slots -> baselines (canonical order), then number the slots internally ----
   pl->grp_ncomp.assign(d->group_ncomp, d->group_ncomp + d->ngroups);
   pl->grp_nslots.assign(d->group_nslots, d->group_nslots + d->ngroups);
   pl->grp_slot0.resize(d->ngroups);
   pl->grp_coef0.resize(d->ngroups);
-  long long ns = 0, nc = 0;
+  std::vector<long long> canon_slot0(d->ngroups);
+  long long ns = 0, nc = 0, nh = 0;
   for (int g = 0; g < d->ngroups; ++g) {
-    if (d->group_ncomp[g] < 0 || d->group_nslots[g] <= 0) {
-      delete pl;
-      return fail(CALB2_ERR_ARG, "group %d: bad ncomp/nslots", g);
-    }
-    pl->grp_slot0[g] = (int)ns;
+    canon_slot0[g] = ns;
     pl->grp_coef0[g] = (int)nc;
     if (d->group_nslots[g] != 1) pl->all_single_slot = false;
     ns += d->group_nslots[g];
     nc += d->group_ncomp[g];
+    if (grp_cls[g] < 0) nh += d->group_nslots[g];
   }
   pl->nslots = ns;
   pl->ncoef = nc;
-  pl->slot_nbls.assign(d->slot_nbls, d->slot_nbls + ns);
+  pl->nslots_heavy = nh;
+  pl->nslots_class = ns - nh;
+  {
+    long long next_h = 0;
+    for (int g = 0; g < d->ngroups; ++g)
+      if (grp_cls[g] < 0) {
+        pl->grp_slot0[g] = (int)next_h;
+        next_h += d->group_nslots[g];
+      }
+    long long next_c = nh;
+    for (auto& mem : cls_members)
+      for (int g : mem) pl->grp_slot0[g] = (int)next_c++;
+  }
+  std::vector<long long> canon_bl0(ns + 1);
+  long long nb = 0;
+  for (long long s = 0; s < ns; ++s) {
+    canon_bl0[s] = nb;
+    if (d->slot_nbls[s] <= 0) {
+      delete pl;
+      return fail(CALB2_ERR_ARG, "slot %lld: no baselines", s);
+    }
+    nb += d->slot_nbls[s];
+  }
+  canon_bl0[ns] = nb;
+  pl->nbls = nb;
+  pl->slot_nbls.resize(ns);
   pl->slot_grp.resize(ns);
   pl->slot_bl0.resize(ns + 1);
-  long long nb = 0;
   for (int g = 0; g < d->ngroups; ++g)
-    for (int s = 0; s < d->group_nslots[g]; ++s) pl->slot_grp[pl->grp_slot0[g] + s] = g;
-  for (long long s = 0; s < ns; ++s) {
-    pl->slot_bl0[s] = (int)nb;
-    if (pl->slot_nbls[s] != 1) pl->all_single_bl = false;
-    nb += pl->slot_nbls[s];
-  }
-  pl->slot_bl0[ns] = (int)nb;
-  pl->nbls = nb;
+    for (int s = 0; s < d->group_nslots[g]; ++s) {
+      const long long cs = canon_slot0[g] + s, is = pl->grp_slot0[g] + s;
+      pl->slot_grp[is] = g;
+      pl->slot_nbls[is] = d->slot_nbls[cs];
+      pl->slot_bl0[is] = (int)canon_bl0[cs];
+      if (d->slot_nbls[cs] != 1) {
+        pl->all_single_bl = false;
+        (grp_cls[g] < 0 ? pl->heavy_single_bl : pl->cls_single_bl) = false;
+      }
+    }
+  pl->slot_bl0[ns] = (int)nb;  // only meaningful when the numbering is canonical (the generic path)
   pl->bl_ant0.assign(d->bl_ant0, d->bl_ant0 + nb);
   pl->bl_ant1.assign(d->bl_ant1, d->bl_ant1 + nb);
   for (long long b = 0; b < nb; ++b)
@@ -788,11 +939,11 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     }
   pl->bl_slot.resize(nb);
   for (long long s = 0; s < ns; ++s)
-    for (int b = pl->slot_bl0[s]; b < pl->slot_bl0[s + 1]; ++b) pl->bl_slot[b] = (int)s;
+    for (int b = pl->slot_bl0[s]; b < pl->slot_bl0[s] + pl->slot_nbls[s]; ++b) pl->bl_slot[b] = (int)s;
 
-  // ---- pack slots into items (one CTA each): rows <= KMAX, slots <= SMAX ----
+  // ---- streaming path: pack its slots into items (one CTA each): rows <= KMAX, slots <= SMAX ----
   pl->slot_row0.resize(ns + 1);
-  pl->slot_item.resize(ns);
+  pl->slot_item.assign(ns, -1);
   std::vector<unsigned char> row_slot;
   std::vector<int> row_coef;
   ItemDesc cur{};
@@ -805,7 +956,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     a_off += (long long)cur.nrows * pl->nfp;
     cur = ItemDesc{};
   };
-  for (long long s = 0; s < ns; ++s) {
+  for (long long s = 0; s < nh; ++s) {
     const int g = pl->slot_grp[s];
     const int ncomp = pl->grp_ncomp[g];
     const int rp = std::max(G, ((ncomp + G - 1) / G) * G);  // at least one step so the slot exists in the item
@@ -843,11 +994,62 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
       new_index[order[n]] = (int)n;
     }
     pl->items.swap(sorted);
-    for (long long s = 0; s < ns; ++s) pl->slot_item[s] = new_index[pl->slot_item[s]];
+    for (long long s = 0; s < nh; ++s) pl->slot_item[s] = new_index[pl->slot_item[s]];
+  }
+  const long long heavy_rows = rows;
+  const long long heavy_floats = heavy_rows * (long long)pl->nfp;
+
+  // ---- shared-basis path: one block per class after the streaming tiles; backward-sum rows after the streaming rows ----
+  std::vector<ClassSlot> cslots;
+  std::vector<int> cs_slot;
+  {
+    long long off = heavy_floats;
+    for (auto& mem : cls_members) {
+      calb2_plan::ClsInfo ci{};
+      ci.ncomp = pl->grp_ncomp[mem[0]];
+      ci.kp = ((ci.ncomp + 7) / 8) * 8;
+      ci.nmembers = (int)mem.size();
+      ci.a_off = off;
+      ci.uploaded = false;
+      off += (long long)ci.kp * pl->nfp;
+      const int first_cs = (int)cslots.size();
+      for (int g : mem) {
+        const int is = pl->grp_slot0[g];
+        pl->slot_row0[is] = (int)rows;
+        ClassSlot cs{};
+        cs.coef0 = pl->grp_coef0[g];
+        cs.row0 = (int)rows;
+        cs.bl0 = pl->slot_bl0[is];
+        cs.nb = pl->slot_nbls[is];
+        cslots.push_back(cs);
+        cs_slot.push_back(is);
+        rows += ci.ncomp;
+        pl->n_a_nz += (long long)ci.ncomp * pl->nf;
+      }
+      for (int v = 0; v < 2; ++v) {
+        const int MSv = v == 0 ? 64 : 32;
+        for (int m0 = 0; m0 < (int)mem.size(); m0 += MSv) {
+          MTileDesc mt{};
+          mt.a_off = ci.a_off;
+          mt.kp = ci.kp;
+          mt.ncomp = ci.ncomp;
+          mt.nslots = std::min(MSv, (int)mem.size() - m0);
+          mt.cs0 = first_cs + m0;
+          pl->mtiles[v].push_back(mt);
+        }
+      }
+      pl->classes.push_back(ci);
+    }
+    pl->a_class_floats = off - heavy_floats;
+    for (int v = 0; v < 2; ++v)  // longest first: cost ~ rows x (16-group blocks in use)
+      std::stable_sort(pl->mtiles[v].begin(), pl->mtiles[v].end(), [](const MTileDesc& a, const MTileDesc& b) {
+        const long long ca = (long long)a.kp * ((a.nslots + 15) / 16), cb = (long long)b.kp * ((b.nslots + 15) / 16);
+        return ca > cb;
+      });
   }
   pl->slot_row0[ns] = (int)rows;
   pl->rows_total = rows;
-  pl->a_floats = rows * (long long)pl->nfp;
+  pl->a_floats = heavy_floats + pl->a_class_floats;
   if (nb * (long long)pl->nfp > INT_MAX) {
     delete pl;
     return fail(CALB2_ERR_UNSUPPORTED, "nbls * nfreqs = %lld exceeds the 32-bit element index of the fused kernel", nb * (long long)pl->nfp);
@@ -882,10 +1084,19 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
 
   std::vector<SlotGeom> geom(ns);
   for (long long s = 0; s < ns; ++s) {
-    const ItemDesc& item = pl->items[pl->slot_item[s]];
-    geom[s].a_off = item.a_off;
-    geom[s].item_rows = item.nrows;
-    geom[s].row_in_item = pl->slot_row0[s] - item.row0;
+    const int cls = grp_cls[pl->slot_grp[s]];
+    if (cls < 0) {
+      const ItemDesc& item = pl->items[pl->slot_item[s]];
+      geom[s].a_off = item.a_off;
+      geom[s].item_rows = item.nrows;
+      geom[s].row_in_item = pl->slot_row0[s] - item.row0;
+      geom[s].swz_ft = 0;
+    } else {
+      geom[s].a_off = pl->classes[cls].a_off;
+      geom[s].item_rows = pl->classes[cls].kp;
+      geom[s].row_in_item = 0;
+      geom[s].swz_ft = SharedCfg<64, 2>::FT;
+    }
     geom[s].nbls = pl->slot_nbls[s];
   }
 
@@ -934,6 +1145,10 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(upload(pl->row_coef, row_coef, pl));
   TRY(upload(pl->d_slot_row0, pl->slot_row0, pl));
   TRY(upload(pl->d_slot_bl0, pl->slot_bl0, pl));
+  TRY(upload(pl->d_slot_nb, pl->slot_nbls, pl));
+  for (int v = 0; v < 2; ++v) TRY(upload(pl->d_mtiles[v], pl->mtiles[v], pl));
+  TRY(upload(pl->d_cslots, cslots, pl));
+  TRY(upload(pl->d_cs_slot, cs_slot, pl));
   TRY(upload(pl->d_bl_ant0, pl->bl_ant0, pl));
   TRY(upload(pl->d_bl_ant1, pl->bl_ant1, pl));
   TRY(upload(pl->d_bl_slot, pl->bl_slot, pl));
@@ -967,7 +1182,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(dalloc(pl->cm_i, (size_t)nc, pl));
   TRY(dalloc(pl->cu_i, (size_t)nc, pl));
   TRY(dalloc(pl->dcpart, (size_t)rows * 4, pl));
-  TRY(dalloc(pl->partials, pl->items.size() * 4, pl));
+  TRY(dalloc(pl->partials, (pl->items.size() + std::max(pl->mtiles[0].size(), pl->mtiles[1].size())) * 4, pl));
   TRY(dalloc(pl->red_d, 4096, pl));
   TRY(dalloc(pl->dbg_out, 16, pl));
   TRY(dalloc(pl->state, 1, pl));
@@ -1014,6 +1229,10 @@ int calb2_plan_destroy(calb2_plan* pl) {
   pl->comm_scalars.release();
   pl->light_partials.release();
   pl->d_items.release();
+  for (int v = 0; v < 2; ++v) pl->d_mtiles[v].release();
+  pl->d_cslots.release();
+  pl->d_cs_slot.release();
+  pl->d_slot_nb.release();
   pl->row_slot.release();
   DevBuf<int>* ib[] = {&pl->row_coef, &pl->d_slot_row0, &pl->d_slot_bl0, &pl->d_bl_ant0, &pl->d_bl_ant1, &pl->d_bl_slot,
                        &pl->ant_ptr, &pl->ant_ent, &pl->ant_partner, &pl->coef_row0, &pl->coef_grp, &pl->d_grp_nslots, &pl->d_grp_slot0,
@@ -1049,6 +1268,16 @@ int calb2_plan_get_info(const calb2_plan* pl, calb2_plan_info* info) {
   info->device_bytes = (int64_t)pl->device_bytes;
   info->generic = pl->gen ? 1 : 0;
   info->dtype = pl->dtype;
+  info->n_classes = (int64_t)pl->classes.size();
+  info->n_class_slots = pl->nslots_class;
+  info->n_class_ctas = (int64_t)pl->mtiles[0].size();
+  info->n_a_class = pl->a_class_floats;
+  info->n_a_class_nz = 0;
+  info->class_fma = 0;
+  for (const auto& ci : pl->classes) {
+    info->n_a_class_nz += (int64_t)ci.ncomp * ci.nmembers * pl->nf;  // what the streaming path would read for these groups
+    info->class_fma += (int64_t)4 * ci.ncomp * ci.nmembers * pl->nf; // forward + backward, real + imaginary part
+  }
   if (pl->gen) {
     info->n_a_stored = pl->n_a_nz;
     info->nitems = 0;
@@ -1090,6 +1319,8 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* con
     if (need == 0) continue;
     if (!blk) return fail(CALB2_ERR_ARG, "group %d: null basis block", g);
     if (need > pl->staging_floats) return fail(CALB2_ERR_UNSUPPORTED, "group %d basis block exceeds the staging buffer", g);
+    const int cls = pl->grp_cls[g];
+    if (cls >= 0 && pl->classes[cls].uploaded) continue;  // shared-basis class: stored once, by its first member
     long long base;
     auto it = seen.find(blk);
     if (it != seen.end()) {
@@ -1102,6 +1333,18 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* con
       seen.emplace(blk, base);
       used += need;
     }
+    if (cls >= 0) {
+      RetileJob jb{};
+      jb.src_off = base;
+      jb.dst_off = pl->classes[cls].a_off;
+      jb.ncomp = ncomp;
+      jb.item_rows = pl->classes[cls].kp;
+      jb.row_in_item = 0;
+      jb.swz_ft = SharedCfg<64, 2>::FT;
+      jobs.push_back(jb);
+      pl->classes[cls].uploaded = true;
+      continue;
+    }
     for (int s = 0; s < nsl; ++s) {
       const int slot = pl->grp_slot0[g] + s;
       const ItemDesc& item = pl->items[pl->slot_item[slot]];
@@ -1111,6 +1354,7 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* con
       jb.ncomp = ncomp;
       jb.item_rows = item.nrows;
       jb.row_in_item = pl->slot_row0[slot] - item.row0;
+      jb.swz_ft = 0;
       jobs.push_back(jb);
     }
   }
@@ -1297,7 +1541,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, double prior_r,
   CU(launch_heavy(pl, sum, hp, (int)pl->items.size(), pl->stream));
   FinalizeParams fp{};
   fp.partials = pl->partials.p;
-  fp.nitems = (int)pl->items.size();
+  fp.nitems = n_partials(pl, sum);
   fp.st = pl->state_eval.p;
   fp.k = k;
   fp.eval_only = 1;

@@ -110,7 +110,8 @@ struct HeavyParams {
   const unsigned char* row_slot;  // [rows_total] slot index local to the item
   const int* row_coef;            // [rows_total] coefficient index, -1 for alignment rows
   const int* slot_row0;           // [nslots_total + 1] global row of each slot's first row
-  const int* slot_bl0;            // [nslots_total + 1] first baseline of each slot
+  const int* slot_bl0;            // [nslots_total] first baseline of each slot
+  const int* slot_nb;             // [nslots_total] baselines of each slot
   const int* bl_ant0;
   const int* bl_ant1;
   const float* d_r;               // [nbls][nfp]
@@ -361,7 +362,8 @@ struct HeavyCfg {
   static constexpr int OFF_STEPSLOT = OFF_CBUF + NWARP * G * RPT_PAD * 8;
   static constexpr int OFF_SLOTSTEP0 = OFF_STEPSLOT + ((NSTEP + 15) / 16) * 16;
   static constexpr int OFF_SLOTBL0 = OFF_SLOTSTEP0 + (SMAX + 1) * 4 + 12;
-  static constexpr int OFF_RED = OFF_SLOTBL0 + (SMAX + 1) * 4 + 12;
+  static constexpr int OFF_SLOTNB = OFF_SLOTBL0 + (SMAX + 1) * 4 + 12;
+  static constexpr int OFF_RED = OFF_SLOTNB + (SMAX + 1) * 4 + 12;
   static constexpr int OFF_MBAR = OFF_RED + NWARP * 4 * 4;
   static constexpr int SMEM_BYTES = OFF_MBAR + NBUF * 8;
 };
@@ -392,6 +394,7 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
   unsigned char* step_slot = smem + C::OFF_STEPSLOT;
   int* slot_step0 = reinterpret_cast<int*>(smem + C::OFF_SLOTSTEP0);
   int* slot_bl0 = reinterpret_cast<int*>(smem + C::OFF_SLOTBL0);
+  int* slot_nbs = reinterpret_cast<int*>(smem + C::OFF_SLOTNB);
   float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::OFF_MBAR);
 
@@ -437,7 +440,10 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
   for (int s = tid; s < nsteps; s += C::NTHR) step_slot[s] = p.row_slot[it.row0 + s * G];
   for (int s = tid; s <= it.nslots; s += C::NTHR) {
     slot_step0[s] = (p.slot_row0[it.slot0 + s] - it.row0) / G;
-    slot_bl0[s] = p.slot_bl0[it.slot0 + s];
+    if (s < it.nslots) {
+      slot_bl0[s] = p.slot_bl0[it.slot0 + s];
+      slot_nbs[s] = p.slot_nb[it.slot0 + s];
+    }
   }
   __syncthreads();
 
@@ -484,7 +490,7 @@ __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
       q_vp[m] = (s * 2) * FT + f;        // partial of warp w: + w * 2 * FT (real), + FT more (imaginary)
       q_qb[m] = (s * NQ) * FT + f;
       q_b0[m] = b;
-      q_nb[m] = slot_bl0[s + 1] - b;
+      q_nb[m] = slot_nbs[s];
       q_vo[m] = (it.slot0 + s) * p.nfp + f;
       if (q_nb[m] > 0) {
         qoff[m] = b * p.nfp + f;
@@ -1294,18 +1300,22 @@ struct RetileJob {
   int ncomp;
   int item_rows;
   int row_in_item;
-  int pad;
+  int swz_ft;         // 0: streaming-path tiles of the plan's width; 32: shared-basis block, swizzled 32-channel tiles
 };
 
-// staging [ncomp][nfreqs] row-major  ->  tiled [tile][item_rows][FT]
+// staging [ncomp][nfreqs] row-major  ->  tiled [tile][item_rows][FT]  (shared-basis blocks: FT = 32, 16-byte chunks
+// XOR-swizzled with the row index, see calfit_shared.cuh)
 __global__ void retile_kernel(const float* __restrict__ staging, float* __restrict__ A, const RetileJob* jobs,
                               int nfreqs, int ft) {
   const RetileJob jb = jobs[blockIdx.x];
   const long long n = (long long)jb.ncomp * nfreqs;
+  const int w = jb.swz_ft ? jb.swz_ft : ft;
   for (long long e = threadIdx.x; e < n; e += blockDim.x) {
     const int k = (int)(e / nfreqs), f = (int)(e % nfreqs);
-    const int tile = f / ft, fi = f % ft;
-    A[jb.dst_off + ((long long)tile * jb.item_rows + jb.row_in_item + k) * ft + fi] = staging[jb.src_off + e];
+    const int tile = f / w, row = jb.row_in_item + k;
+    int fi = f % w;
+    if (jb.swz_ft) fi = (((fi >> 2) ^ (row & 7)) << 2) | (fi & 3);
+    A[jb.dst_off + ((long long)tile * jb.item_rows + row) * w + fi] = staging[jb.src_off + e];
   }
 }
 

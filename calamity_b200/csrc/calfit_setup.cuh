@@ -19,12 +19,22 @@ struct GramJob {
 };
 
 struct SlotGeom {
-  long long a_off;     // float offset of the owning item's tile 0
+  long long a_off;     // float offset of the owning item's (or basis class's) tile 0
   int item_rows;
   int row_in_item;
   int nbls;
-  int pad;
+  int swz_ft;          // 0: [tile][item_rows][ft] of the streaming path; 32: shared-basis block, 32-channel tiles with the
+                       // 128-byte XOR swizzle (16-byte chunk index ^ (row & 7)) of calfit_shared.cuh
 };
+
+// float offset of basis element (row k of the slot, channel f) in the tiled basis
+__device__ __forceinline__ long long basis_elem_offset(const SlotGeom& sg, int k, int f, int ft) {
+  if (sg.swz_ft) {
+    const int row = sg.row_in_item + k, fi = f % sg.swz_ft;
+    return sg.a_off + ((long long)(f / sg.swz_ft) * sg.item_rows + row) * sg.swz_ft + ((((fi >> 2) ^ (row & 7)) << 2) | (fi & 3));
+  }
+  return sg.a_off + ((long long)(f / ft) * sg.item_rows + sg.row_in_item + k) * ft + (f % ft);
+}
 
 // Gram matrix of the dense design matrix of calibration.py:897: every baseline of a slot repeats the
 // slot's rows, so G[k][k'] = sum_slots nbls_slot * sum_f U[k, slot, f] U[k', slot, f].
@@ -66,7 +76,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ A, 
         for (int e = threadIdx.x; e < n * FC; e += 256) {
           const int k = e / FC, fi = e % FC, f = f0 + fi;
           float v = 0.f;
-          if (f < nfreqs) v = A[sg.a_off + ((long long)(f / ft) * sg.item_rows + sg.row_in_item + k) * ft + (f % ft)];
+          if (f < nfreqs) v = A[basis_elem_offset(sg, k, f, ft)];
           tile[k * (FC + 1) + fi] = v;
         }
         __syncthreads();

@@ -1,0 +1,407 @@
+// Shared-basis path of the fused fit kernel (sm_100a).
+//
+// In the reference's per-baseline DPSS layout every baseline is its own fitting group, but the basis only depends on
+// the baseline's integer-nanosecond delay (modeling.py:293; operator cache modeling.py:352, 371): at HERA-350 the
+// 61 075 groups share 120 distinct bases (16 036 distinct rows, 66 MB -- L2-resident), ~509 groups each.  The
+// streaming kernel of calfit_kernels.cuh reads one private copy per group (25 GB per iteration).  Here every distinct
+// basis ("class") is stored ONCE, and a CTA takes MS groups of one class through all channels, so that per staged
+// [kp rows x 32 channels] tile the contraction is a small GEMM on the CUDA cores with register-tiled operands:
+//
+//   phase F   V[2 MS x 32]   = C[2 MS x kp] . A[kp x 32]          (calibration.py:1587-1590; rows = (part, group))
+//   phase Q   per (group, channel): gains, model, weighted residual, chi^2, z, dL/dv  (calibration.py:1593-1609)
+//   phase B   dC[NQ MS x kp] += Q[NQ MS x 32] . A[kp x 32]^T       (coefficient half of the tape gradient, 664-666)
+//
+// The dC accumulators stay in registers across all tiles of the CTA (one thread owns an 8 x TK block of
+// (row, vector) pairs for the whole pass: no cross-thread reduction, deterministic), the tile comes in by one bulk
+// asynchronous copy (TMA engine) per buffer with mbarrier double buffering, exactly like the streaming kernel.
+// The tile is stored with the 128-byte XOR swizzle (16-byte chunk index ^ (row & 7)), which makes both the row-wise
+// reads of phase F and the column-of-rows reads of phase B bank-conflict free (and is the layout a tcgen05 / TMA
+// SWIZZLE_128B descriptor expects, should the contraction move to the tensor cores).
+//
+// DRAM traffic per iteration drops from 4 N_A_nz + 12 N_D to ~12 N_D + 8 N_D (z) + the parameters; the kernel is
+// bound by the FP32 FMA pipe (8 N_A_nz flops), not by HBM.
+#pragma once
+#include "calfit_kernels.cuh"
+
+namespace calb2 {
+
+struct MTileDesc {
+  long long a_off;  // float offset of the class's tile 0: [ntiles][kp][32], swizzled
+  int kp;           // staged rows: ncomp rounded up to 8 (padding rows are zero)
+  int ncomp;
+  int nslots;       // groups of the class taken by this CTA, <= MS
+  int cs0;          // first entry of the CTA in the class-slot tables
+};
+
+struct ClassSlot {
+  int coef0;  // first coefficient of the group
+  int row0;   // row of the group's first backward sum in dcpart
+  int bl0;    // first baseline of the slot
+  int nb;     // baselines of the slot (redundant baselines share the model visibility)
+};
+
+struct SharedParams {
+  const float* A;
+  const MTileDesc* tiles;
+  const ClassSlot* cslots;
+  const int* cs_slot;   // global slot index (row of vout)
+  const int* bl_ant0;
+  const int* bl_ant1;
+  const float* d_r;
+  const float* d_i;
+  const float* w;
+  const float* g_r[2];
+  const float* g_i[2];
+  const float* c_r;
+  const float* c_i;
+  float2* z;
+  float2* y;
+  float* dcpart;
+  float2* vout;
+  double* partials;     // [gridDim.x][4], already offset past the streaming kernel's items
+  const FitState* st;
+  int nfp;
+  int ntiles;           // nfp / 32
+  int store_v;          // forward only, model visibilities -> vout
+  int init_mode;        // backward only, dL/dv := data * (w != 0)   (coefficient initialisation, calibration.py:875-902)
+};
+
+template <int MS_, int NQ_>
+struct SharedCfg {
+  static constexpr int MS = MS_;            // groups per CTA
+  static constexpr int NQ = NQ_;            // backward sums per group: 2, or 4 with the 'sum' regulariser
+  static constexpr int NTHR = 256;
+  static constexpr int FT = 32;             // channels per tile = one 128-byte swizzle row
+  static constexpr int MF = 2 * MS;         // forward rows (part-major: row = part * MS + group)
+  static constexpr int MB = NQ * MS;        // backward rows (row = q * MS + group)
+  static constexpr int MPT = MF / 32;       // forward rows per thread
+  static constexpr int TKMAX = 13;          // vectors per thread in phase B; kp <= 16 * TK
+  static constexpr int KROWS = 16 * TKMAX;
+  static constexpr int CT_PITCH = MF + 4;   // coefficients, [k][row]: + 4 keeps the staging writes at 4-way conflicts
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_CT = OFF_A + 2 * KROWS * FT * 4;
+  static constexpr int OFF_V = OFF_CT + KROWS * CT_PITCH * 4;
+  static constexpr int OFF_Q = OFF_V + MF * FT * 4;
+  static constexpr int OFF_CS = OFF_Q + MB * FT * 4;
+  static constexpr int OFF_ANT = OFF_CS + MS * 16;
+  static constexpr int OFF_GSLOT = OFF_ANT + MS * 8;
+  static constexpr int OFF_RED = OFF_GSLOT + MS * 4;
+  static constexpr int OFF_MBAR = OFF_RED + 8 * 4 * 4;
+  static constexpr int SMEM_BYTES = OFF_MBAR + 2 * 8;
+  static_assert(MB == 128, "phase B is laid out for 128 rows");
+  static_assert(MPT == 2 || MPT == 4, "phase F handles 2 or 4 rows per thread");
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int MS, int NQ, bool SINGLE, int TK>
+__device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDesc& mt, unsigned char* smem) {
+  using C = SharedCfg<MS, NQ>;
+  constexpr int FT = C::FT, MPT = C::MPT, PITCH = C::CT_PITCH;
+  constexpr bool SUM = NQ == 4;
+  const FitState* st = p.st;
+  const int gsel = st->step & 1;
+  const float* __restrict__ g_r = p.g_r[gsel];
+  const float* __restrict__ g_i = p.g_i[gsel];
+
+  float* Abuf = reinterpret_cast<float*>(smem + C::OFF_A);
+  float* CT = reinterpret_cast<float*>(smem + C::OFF_CT);
+  float* Vs = reinterpret_cast<float*>(smem + C::OFF_V);
+  float* Qs = reinterpret_cast<float*>(smem + C::OFF_Q);
+  ClassSlot* s_cs = reinterpret_cast<ClassSlot*>(smem + C::OFF_CS);
+  int2* s_ant = reinterpret_cast<int2*>(smem + C::OFF_ANT);
+  int* s_gslot = reinterpret_cast<int*>(smem + C::OFF_GSLOT);
+  float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::OFF_MBAR);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kp = mt.kp, nslots = mt.nslots;
+  const uint32_t tile_bytes = (uint32_t)kp * FT * 4u;
+  const float* Abase = p.A + mt.a_off;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+    mbar_expect_tx(&mbar[0], tile_bytes);
+    bulk_g2s(Abuf, Abase, tile_bytes, &mbar[0]);
+    if (p.ntiles > 1) {
+      mbar_expect_tx(&mbar[1], tile_bytes);
+      bulk_g2s(Abuf + C::KROWS * FT, Abase + (size_t)kp * FT, tile_bytes, &mbar[1]);
+    }
+  }
+  // rows kp .. 16 TK - 1 are never written by the bulk copies: zero them once (phase B reads 16 TK rows)
+  {
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int tail4 = (16 * TK - kp) * FT / 4;
+    for (int e = tid; e < tail4; e += C::NTHR) {
+      reinterpret_cast<float4*>(Abuf + kp * FT)[e] = zero4;
+      reinterpret_cast<float4*>(Abuf + C::KROWS * FT + kp * FT)[e] = zero4;
+    }
+    // dL/dv rows of the groups this CTA does not have stay zero for the whole pass
+    for (int e = tid; e < C::MB * FT / 4; e += C::NTHR) reinterpret_cast<float4*>(Qs)[e] = zero4;
+  }
+  if (tid < MS) {
+    ClassSlot cs = {0, 0, 0, 0};
+    int gs = 0;
+    int2 ants = make_int2(0, 0);
+    if (tid < nslots) {
+      cs = p.cslots[mt.cs0 + tid];
+      gs = p.cs_slot[mt.cs0 + tid];
+      ants = make_int2(p.bl_ant0[cs.bl0], p.bl_ant1[cs.bl0]);
+    }
+    s_cs[tid] = cs;
+    s_gslot[tid] = gs;
+    s_ant[tid] = ants;
+  }
+  __syncthreads();
+  // coefficients of the CTA's groups, transposed to [k][row] so that phase F reads its rows with one LDS.128 / LDS.64
+  if (!p.init_mode) {
+    for (int m = warp; m < C::MF; m += 8) {
+      const int part = m / MS, s = m % MS;
+      const bool valid = s < nslots;
+      const float* src = (part ? p.c_i : p.c_r) + s_cs[s].coef0;
+      for (int k = lane; k < kp; k += 32) CT[k * PITCH + m] = (valid && k < mt.ncomp) ? src[k] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- thread roles ----
+  // phase F: 8 chunk lanes x 32 row groups; a warp owns 4 MPT consecutive rows = one part, MPT*4 consecutive groups
+  const int f_fg = tid & 7, f_m0 = (tid >> 3) * MPT;
+  const bool f_active = !p.init_mode && ((warp * 4 * MPT) % MS) < nslots;
+  // phase B: 16 vector lanes x 16 row groups of 8; a warp owns 16 consecutive rows = one q, 16 consecutive groups
+  const int b_kg = tid & 15, b_m0 = (tid >> 4) * 8;
+  const bool b_active = !p.store_v && ((warp * 16) % MS) < nslots;
+  const int b_sw = b_kg & 7;
+
+  float acc[8][TK];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int t = 0; t < TK; ++t) acc[i][t] = 0.f;
+  float loss_acc = 0.f, sr_acc = 0.f, si_acc = 0.f;
+
+  for (int j = 0; j < p.ntiles; ++j) {
+    const int buf = j & 1;
+    mbar_wait(&mbar[buf], (j >> 1) & 1);
+    const float* Ab = Abuf + buf * C::KROWS * FT;
+
+    // ---------------- phase F ----------------
+    if (f_active) {
+      float4 v[MPT];
+#pragma unroll
+      for (int i = 0; i < MPT; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* ctp = CT + f_m0;
+      for (int k0 = 0; k0 < kp; k0 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k0 + u;
+          const float4 a = *reinterpret_cast<const float4*>(Ab + k * FT + ((f_fg ^ u) << 2));
+          if constexpr (MPT == 4) {
+            const float4 c = *reinterpret_cast<const float4*>(ctp + k * PITCH);
+            axpy4(c.x, a, v[0]);
+            axpy4(c.y, a, v[1]);
+            axpy4(c.z, a, v[2]);
+            axpy4(c.w, a, v[3]);
+          } else {
+            const float2 c = *reinterpret_cast<const float2*>(ctp + k * PITCH);
+            axpy4(c.x, a, v[0]);
+            axpy4(c.y, a, v[1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MPT; ++i) *reinterpret_cast<float4*>(Vs + (f_m0 + i) * FT + f_fg * 4) = v[i];
+    }
+    __syncthreads();
+
+    // ---------------- phase Q: lane = channel, warp w takes groups w, w + 8, ... ----------------
+    {
+      const int fo = j * FT + lane;
+#pragma unroll
+      for (int h = 0; h < MS / 8; h += 4) {
+        float in[4][7];
+        int bl[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {  // all loads of four groups first
+          const int s = warp + 8 * (h + n);
+          bl[n] = -1;
+          if (s < nslots) {
+            const ClassSlot cs = s_cs[s];
+            bl[n] = cs.bl0;
+            const size_t o = (size_t)cs.bl0 * p.nfp + fo;
+            in[n][0] = p.d_r[o];
+            in[n][1] = p.d_i[o];
+            in[n][2] = p.w[o];
+            if (!p.init_mode && !p.store_v) {
+              const int2 an = s_ant[s];
+              const size_t o0 = (size_t)an.x * p.nfp + fo, o1 = (size_t)an.y * p.nfp + fo;
+              in[n][3] = g_r[o0];
+              in[n][4] = g_i[o0];
+              in[n][5] = g_r[o1];
+              in[n][6] = g_i[o1];
+            }
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int s = warp + 8 * (h + n);
+          if (bl[n] < 0) continue;
+          float qr = 0.f, qi = 0.f, pw = 0.f, qw = 0.f;
+          if (p.init_mode) {  // right-hand side of the coefficient initialisation: data * (w != 0)
+            const float msk0 = (fabsf(in[n][2]) <= 1e-8f) ? 0.f : 1.f;  // np.isclose(w, 0): |w| <= atol = 1e-8
+            qr = in[n][0] * msk0;
+            qi = in[n][1] * msk0;
+            if (!SINGLE) {
+              const int nb = s_cs[s].nb;
+              for (int b = 1; b < nb; ++b) {
+                const size_t o = (size_t)(bl[n] + b) * p.nfp + fo;
+                const float msk = (fabsf(p.w[o]) <= 1e-8f) ? 0.f : 1.f;
+                qr += p.d_r[o] * msk;
+                qi += p.d_i[o] * msk;
+              }
+            }
+          } else {
+            const float v_r = Vs[s * FT + lane], v_i = Vs[(MS + s) * FT + lane];
+            if (p.store_v) {
+              p.vout[(size_t)s_gslot[s] * p.nfp + fo] = make_float2(v_r, v_i);
+              continue;
+            }
+            // one visibility: model = g_i conj(g_j) v, weighted residual, chi^2, z, dL/dv (calibration.py:1593-1609)
+            auto visibility = [&](size_t o, float dr, float di, float w, float gr0, float gi0, float gr1, float gi1) {
+              const float P = gr0 * gr1 + gi0 * gi1;
+              const float Q = gr0 * gi1 - gi0 * gr1;
+              const float mr = P * v_r + Q * v_i;
+              const float mi = P * v_i - Q * v_r;
+              const float rr = dr - mr, ri = di - mi;
+              loss_acc += (rr * rr + ri * ri) * w;
+              const float er = -2.f * w * rr, ei = -2.f * w * ri;
+              p.z[o] = make_float2(er * v_r + ei * v_i, er * v_i - ei * v_r);
+              qr += P * er - Q * ei;
+              qi += Q * er + P * ei;
+              if (SUM) {
+                p.y[o] = make_float2(w * v_r, w * v_i);
+                sr_acc += w * mr;
+                si_acc += w * mi;
+                pw += P * w;
+                qw += Q * w;
+              }
+            };
+            visibility((size_t)bl[n] * p.nfp + fo, in[n][0], in[n][1], in[n][2], in[n][3], in[n][4], in[n][5], in[n][6]);
+            if (!SINGLE) {
+              const int nb = s_cs[s].nb;
+              for (int b = 1; b < nb; ++b) {
+                const int bb = bl[n] + b;
+                const size_t o = (size_t)bb * p.nfp + fo;
+                const size_t o0 = (size_t)p.bl_ant0[bb] * p.nfp + fo, o1 = (size_t)p.bl_ant1[bb] * p.nfp + fo;
+                visibility(o, p.d_r[o], p.d_i[o], p.w[o], g_r[o0], g_i[o0], g_r[o1], g_i[o1]);
+              }
+            }
+          }
+          Qs[s * FT + lane] = qr;
+          Qs[(MS + s) * FT + lane] = qi;
+          if (SUM) {
+            Qs[(2 * MS + s) * FT + lane] = pw;
+            Qs[(3 * MS + s) * FT + lane] = qw;
+          }
+        }
+      }
+      // next tile's data / weight rows towards L2 while phase B runs
+      if (j + 1 < p.ntiles && tid < 3 * MS) {
+        const int arr = tid / MS, s = tid % MS;
+        if (s < nslots) {
+          const float* base = arr == 0 ? p.d_r : (arr == 1 ? p.d_i : p.w);
+          prefetch_l2(base + (size_t)s_cs[s].bl0 * p.nfp + (j + 1) * FT);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------- phase B ----------------
+    if (b_active) {
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 q4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q4[i] = *reinterpret_cast<const float4*>(Qs + (b_m0 + i) * FT + c4 * 4);
+        const float* ap = Ab + b_kg * FT + ((c4 ^ b_sw) << 2);
+#pragma unroll
+        for (int t = 0; t < TK; ++t) {
+          const float4 a = *reinterpret_cast<const float4*>(ap + t * 16 * FT);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i][t] = dot4(a, q4[i], acc[i][t]);
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with the tile buffer (and with Vs / Qs): refill it with tile j + 2
+    if (tid == 0 && j + 2 < p.ntiles) {
+      mbar_expect_tx(&mbar[buf], tile_bytes);
+      bulk_g2s(Abuf + buf * C::KROWS * FT, Abase + (size_t)(j + 2) * kp * FT, tile_bytes, &mbar[buf]);
+    }
+  }
+
+  // ---------------- backward sums: thread-private, no reduction ----------------
+  if (b_active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mb = b_m0 + i, q = mb / MS, s = mb % MS;
+      if (s < nslots) {
+        float* dst = p.dcpart + (size_t)s_cs[s].row0 * NQ + q;
+#pragma unroll
+        for (int t = 0; t < TK; ++t) {
+          const int k = b_kg + 16 * t;
+          if (k < mt.ncomp) dst[(size_t)k * NQ] = acc[i][t];
+        }
+      }
+    }
+  }
+
+  // ---------------- per-CTA partial sums (fixed order -> deterministic) ----------------
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+    sr_acc += __shfl_xor_sync(0xffffffffu, sr_acc, off);
+    si_acc += __shfl_xor_sync(0xffffffffu, si_acc, off);
+  }
+  if (lane == 0) {
+    red[warp * 4 + 0] = loss_acc;
+    red[warp * 4 + 1] = sr_acc;
+    red[warp * 4 + 2] = si_acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      a += (double)red[w * 4 + 0];
+      b += (double)red[w * 4 + 1];
+      c += (double)red[w * 4 + 2];
+    }
+    double* dst = p.partials + (size_t)blockIdx.x * 4;
+    dst[0] = a;
+    dst[1] = b;
+    dst[2] = c;
+  }
+}
+
+template <int MS, int NQ, bool SINGLE>
+__global__ void __launch_bounds__(256, 1) shared_kernel(const SharedParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_sh[];
+  const FitState* st = p.st;
+  if (st->step > st->stop_after) return;  // fit already stopped (uniform across the grid)
+  const MTileDesc mt = p.tiles[blockIdx.x];
+  const int tk = (mt.kp + 15) >> 4;
+  if (tk <= 2)
+    shared_body<MS, NQ, SINGLE, 2>(p, mt, smem_sh);
+  else if (tk <= 4)
+    shared_body<MS, NQ, SINGLE, 4>(p, mt, smem_sh);
+  else if (tk <= 6)
+    shared_body<MS, NQ, SINGLE, 6>(p, mt, smem_sh);
+  else if (tk <= 8)
+    shared_body<MS, NQ, SINGLE, 8>(p, mt, smem_sh);
+  else if (tk <= 10)
+    shared_body<MS, NQ, SINGLE, 10>(p, mt, smem_sh);
+  else
+    shared_body<MS, NQ, SINGLE, 13>(p, mt, smem_sh);
+}
+
+}  // namespace calb2

@@ -35,7 +35,7 @@ class FitPlan:
     """Device-resident basis + per-integration state.  Mirrors calibration.py:1143-1152 (create) and
     the per-integration calls of 1184-1300."""
 
-    def __init__(self, layout, device=0, tile_freqs=0, basis_batch=2048):
+    def __init__(self, layout, device=0, tile_freqs=0, basis_batch=2048, shared_basis=0):
         self._lib = nat.load()
         self.layout = layout
         # float32: the fused sm_100a kernels; float64 (precision=64): the generic device path
@@ -48,6 +48,8 @@ class FitPlan:
             group_ncomp=nat.iptr(layout.group_ncomp), group_nslots=nat.iptr(layout.group_nslots),
             slot_nbls=nat.iptr(layout.slot_nbls), bl_ant0=nat.iptr(layout.bl_ant0), bl_ant1=nat.iptr(layout.bl_ant1),
             tile_freqs=tile_freqs, dtype=nat.DTYPE_IDS[self.dtype],
+            # groups with identical basis blocks: stored once, fitted by the shared-basis kernel (0 auto, 1 all, -1 never)
+            group_class=nat.iptr(layout.group_class), shared_basis=int(shared_basis),
         )
         nat.check(self._lib.calb2_plan_create(C.byref(desc), C.byref(self._handle)))
         for g0 in range(0, layout.ngroups, basis_batch):

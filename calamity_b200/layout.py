@@ -44,11 +44,31 @@ class RaggedLayout:
         self.bl_ant0 = np.asarray(self.bl_ant0, dtype=np.int32)
         self.bl_ant1 = np.asarray(self.bl_ant1, dtype=np.int32)
         self.group_coef0 = np.concatenate([[0], np.cumsum(self.group_ncomp)]).astype(np.int64)
+        self.group_class = self._basis_classes()
         self.ngroups = len(self.group_ncomp)
         self.ncoef = int(self.group_coef0[-1])
         self.nbls = len(self.bl_ant0)
         self._finalized = True
         return self
+
+    def _basis_classes(self):
+        """int32 [ngroups]: equal ids <=> identical basis blocks.  modeling.yield_pbl_dpss_model_comps gives every baseline
+        of one integer-ns delay the SAME ndarray (/root/reference/calamity/modeling.py:293, operator cache 352/371), so
+        object identity finds the classes for free; distinct objects are additionally merged by a digest of their bytes
+        (a caller that deep-copied the dict still gets one class per distinct basis)."""
+        import hashlib
+
+        by_obj, by_digest = {}, {}
+        out = np.empty(len(self.blocks), dtype=np.int32)
+        for g, blk in enumerate(self.blocks):
+            cid = by_obj.get(id(blk))
+            if cid is None:
+                a = np.ascontiguousarray(blk)
+                key = (a.shape, a.dtype.str, hashlib.blake2b(a.view(np.uint8).reshape(-1), digest_size=16).digest())
+                cid = by_digest.setdefault(key, len(by_digest))
+                by_obj[id(blk)] = cid
+            out[g] = cid
+        return out
 
     @classmethod
     def from_chunked_dict(cls, chunked, ants_map, nfreqs, nants=None, dtype=np.float32):

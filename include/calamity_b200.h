@@ -74,6 +74,13 @@ typedef struct {
   const int32_t* bl_ant1;       /* [nbls_total] corr_inds[..][1] */
   int32_t tile_freqs;        /* 0 = choose; else 16, 32 or 64 channels per staged tile */
   int32_t dtype;             /* CALB2_F32 or CALB2_F64: element type of every floating point buffer of this plan */
+  /* Shared bases.  modeling.yield_pbl_dpss_model_comps hands the SAME ndarray to every baseline with the same
+   * integer-nanosecond delay (modeling.py:293, operator cache 352/371; 120 distinct arrays for the 61 075 groups of
+   * HERA-350).  group_class[g] >= 0 names the basis block of group g: groups with equal ids MUST have identical blocks
+   * (same ncomp, same values); -1 or a NULL array = private basis.  Single-slot groups of a class with enough members
+   * are stored once and fitted by the shared-basis kernel, everything else by the streaming kernel. */
+  const int32_t* group_class;   /* [ngroups] or NULL */
+  int32_t shared_basis;      /* 0 = automatic (classes of >= 4 groups), 1 = every class, -1 = never (always stream) */
 } calb2_plan_desc;
 
 /* Options of fit_gains_and_foregrounds (calibration.py:447-473). */
@@ -132,6 +139,12 @@ typedef struct {
   int64_t device_bytes;
   int32_t generic;    /* 1: the plan runs the generic unfused path (float64, or a group too large for the fused tile) */
   int32_t dtype;
+  int64_t n_classes;      /* distinct bases stored once (shared-basis path) */
+  int64_t n_class_slots;  /* groups fitted by the shared-basis kernel */
+  int64_t n_class_ctas;   /* its CTAs (64 groups of one class each) */
+  int64_t n_a_class;      /* basis floats resident for the classes (each distinct basis once) */
+  int64_t n_a_class_nz;   /* basis elements those groups count for in n_a_nz (what a per-group copy would hold) */
+  int64_t class_fma;      /* fused multiply-adds of the shared-basis kernel per iteration: 4 * n_a_class_nz */
 } calb2_plan_info;
 
 const char* calb2_last_error(void);

@@ -12,6 +12,9 @@ from tests.helpers import flat_from_synth, long_baseline_subset, mixed_problem, 
 
 pytestmark = pytest.mark.gpu
 F = np.float64
+# both device paths: the streaming kernel (one private basis copy per group) and the shared-basis kernel (each distinct
+# basis stored once; automatic for classes of >= 4 groups)
+PATHS = [pytest.param(dict(shared_basis=-1), id="stream"), pytest.param(dict(shared_basis=0), id="shared")]
 
 
 def _plan(p, **kw):
@@ -86,33 +89,40 @@ def hera350():
     return small_problem("hera350", init_gain_scatter=0.02, coeff_error=0.05)
 
 
-def test_hera128_full_loss_and_gradient(native_built, hera128):
+@pytest.mark.parametrize("path", PATHS)
+def test_hera128_full_loss_and_gradient(native_built, hera128, path):
     """All 8128 baselines x 1024 channels, both regularisations."""
-    info = _check_loss_and_grads(flat_from_synth(hera128))
+    info = _check_loss_and_grads(flat_from_synth(hera128), plan_kw=path)
     assert info["nbls_total"] == 8128
+    assert (info["n_class_slots"] > 8000) == (path["shared_basis"] == 0)
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("reg", [None, "sum"])
-def test_hera128_long_baseline_trajectory(native_built, hera128, reg):
+def test_hera128_long_baseline_trajectory(native_built, hera128, reg, path):
     sub = hera128.select_baselines(long_baseline_subset(hera128, every=6, n_long=300))
-    _check_trajectory(flat_from_synth(sub), reg)
+    _check_trajectory(flat_from_synth(sub), reg, plan_kw=path)
 
 
-def test_hera350_full_loss_and_gradient(native_built, hera350):
-    """The bench workload itself: 61 075 baselines x 1024 channels (26 GB of basis on the streaming path)."""
-    info = _check_loss_and_grads(flat_from_synth(hera350), regs=(None,))
+@pytest.mark.parametrize("path", PATHS)
+def test_hera350_full_loss_and_gradient(native_built, hera350, path):
+    """The bench workload itself: 61 075 baselines x 1024 channels (26 GB of basis on the streaming path, 66 MB on the
+    shared-basis path)."""
+    info = _check_loss_and_grads(flat_from_synth(hera350), regs=(None,) if path["shared_basis"] < 0 else (None, "sum"),
+                                 plan_kw=path)
     assert info["nbls_total"] == 61075
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("reg", [None, "sum"])
-def test_hera350_long_baseline_subset(native_built, hera350, reg):
+def test_hera350_long_baseline_subset(native_built, hera350, reg, path):
     """350 antennas, the 400 longest baselines (ncomp up to 204: five warps per slot, one or two slots per item) and every
     40th of the rest: loss / gradient and a 60-step trajectory."""
     sub = hera350.select_baselines(long_baseline_subset(hera350, every=40, n_long=400))
     assert int(sub.ncomp.max()) == int(hera350.ncomp.max())
     p = flat_from_synth(sub)
-    _check_loss_and_grads(p, regs=(reg,))
-    _check_trajectory(p, reg)
+    _check_loss_and_grads(p, regs=(reg,), plan_kw=path)
+    _check_trajectory(p, reg, plan_kw=path)
 
 
 @pytest.mark.parametrize("ncomp", [300, 400])
@@ -120,6 +130,8 @@ def test_config5_mixed_joint_groups(native_built, ncomp):
     """One joint group of 11 ragged redundant sub-groups (~470 baselines) with 300 vectors (one slot per staged item at 32
     channels per tile) or 400 vectors (forces 16-channel tiles), plus 300 per-baseline DPSS groups."""
     p = mixed_problem(nants=128, nfreqs=1024, seed=7 + ncomp, n_dpss_bls=300, joint=((11, 43, ncomp),))
-    info = _check_loss_and_grads(p)
+    info = _check_loss_and_grads(p)  # hybrid: the joint group streams, DPSS classes of >= 4 baselines share their basis
     assert info["tile_freqs"] == (32 if ncomp <= 352 else 16)
+    assert 0 < info["n_class_slots"] < 300
     _check_trajectory(p, "sum")
+    _check_trajectory(p, "sum", plan_kw=dict(shared_basis=-1))
