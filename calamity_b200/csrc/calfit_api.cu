@@ -810,7 +810,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     std::vector<std::vector<int>> cands;
     for (int g = 0; g < d->ngroups; ++g) {
       const int id = d->group_class[g];
-      if (id < 0 || d->group_nslots[g] != 1 || d->group_ncomp[g] < 1 || d->group_ncomp[g] > SharedCfg<64, 2>::KROWS) continue;
+      if (id < 0 || d->group_nslots[g] != 1 || d->group_ncomp[g] < 1 || d->group_ncomp[g] > SharedCfg<64, 2>::KPMAX) continue;
       auto it = index_of.find(id);
       if (it == index_of.end()) {
         it = index_of.emplace(id, (int)cands.size()).first;

@@ -70,26 +70,29 @@ template <int MS_, int NQ_>
 struct SharedCfg {
   static constexpr int MS = MS_;            // groups per CTA
   static constexpr int NQ = NQ_;            // backward sums per group: 2, or 4 with the 'sum' regulariser
-  static constexpr int NTHR = 256;
+  static constexpr int NTHR = 512;          // 16 warps, 4 per scheduler: enough warps to cover the LDS -> FFMA latency
+  static constexpr int NWARP = NTHR / 32;
   static constexpr int FT = 32;             // channels per tile = one 128-byte swizzle row
   static constexpr int MF = 2 * MS;         // forward rows (part-major: row = part * MS + group)
   static constexpr int MB = NQ * MS;        // backward rows (row = q * MS + group)
-  static constexpr int MPT = MF / 32;       // forward rows per thread
-  static constexpr int TKMAX = 13;          // vectors per thread in phase B; kp <= 16 * TK
-  static constexpr int KROWS = 16 * TKMAX;
+  static constexpr int MPT = MF / 32;       // forward rows per thread (x 4 channels); the two halves of the CTA split k
+  static constexpr int TKMAX = 7;           // vectors per thread in phase B; kp <= 32 * TK
+  static constexpr int KROWS = 32 * TKMAX;  // rows of a tile buffer
+  static constexpr int KPMAX = 208;         // largest class the path takes (HERA-350: 204)
   static constexpr int CT_PITCH = MF + 4;   // coefficients, [k][row]: + 4 keeps the staging writes at 4-way conflicts
   static constexpr int OFF_A = 0;
   static constexpr int OFF_CT = OFF_A + 2 * KROWS * FT * 4;
-  static constexpr int OFF_V = OFF_CT + KROWS * CT_PITCH * 4;
-  static constexpr int OFF_Q = OFF_V + MF * FT * 4;
+  static constexpr int OFF_V = OFF_CT + KPMAX * CT_PITCH * 4;
+  static constexpr int OFF_Q = OFF_V + 2 * MF * FT * 4;
   static constexpr int OFF_CS = OFF_Q + MB * FT * 4;
   static constexpr int OFF_ANT = OFF_CS + MS * 16;
   static constexpr int OFF_GSLOT = OFF_ANT + MS * 8;
   static constexpr int OFF_RED = OFF_GSLOT + MS * 4;
-  static constexpr int OFF_MBAR = OFF_RED + 8 * 4 * 4;
+  static constexpr int OFF_MBAR = OFF_RED + NWARP * 4 * 4;
   static constexpr int SMEM_BYTES = OFF_MBAR + 2 * 8;
   static_assert(MB == 128, "phase B is laid out for 128 rows");
   static_assert(MPT == 2 || MPT == 4, "phase F handles 2 or 4 rows per thread");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -129,10 +132,10 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
       bulk_g2s(Abuf + C::KROWS * FT, Abase + (size_t)kp * FT, tile_bytes, &mbar[1]);
     }
   }
-  // rows kp .. 16 TK - 1 are never written by the bulk copies: zero them once (phase B reads 16 TK rows)
+  // rows kp .. 32 TK - 1 are never written by the bulk copies: zero them once (phase B reads 32 TK rows)
   {
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int tail4 = (16 * TK - kp) * FT / 4;
+    const int tail4 = (32 * TK - kp) * FT / 4;
     for (int e = tid; e < tail4; e += C::NTHR) {
       reinterpret_cast<float4*>(Abuf + kp * FT)[e] = zero4;
       reinterpret_cast<float4*>(Abuf + C::KROWS * FT + kp * FT)[e] = zero4;
@@ -147,7 +150,7 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
     if (tid < nslots) {
       cs = p.cslots[mt.cs0 + tid];
       gs = p.cs_slot[mt.cs0 + tid];
-      ants = make_int2(p.bl_ant0[cs.bl0], p.bl_ant1[cs.bl0]);
+      ants = make_int2(p.bl_ant0[cs.bl0] * p.nfp, p.bl_ant1[cs.bl0] * p.nfp);  // element offsets of the two gain rows
     }
     s_cs[tid] = cs;
     s_gslot[tid] = gs;
@@ -156,7 +159,7 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
   __syncthreads();
   // coefficients of the CTA's groups, transposed to [k][row] so that phase F reads its rows with one LDS.128 / LDS.64
   if (!p.init_mode) {
-    for (int m = warp; m < C::MF; m += 8) {
+    for (int m = warp; m < C::MF; m += C::NWARP) {
       const int part = m / MS, s = m % MS;
       const bool valid = s < nslots;
       const float* src = (part ? p.c_i : p.c_r) + s_cs[s].coef0;
@@ -166,13 +169,15 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
   __syncthreads();
 
   // ---- thread roles ----
-  // phase F: 8 chunk lanes x 32 row groups; a warp owns 4 MPT consecutive rows = one part, MPT*4 consecutive groups
-  const int f_fg = tid & 7, f_m0 = (tid >> 3) * MPT;
-  const bool f_active = !p.init_mode && ((warp * 4 * MPT) % MS) < nslots;
-  // phase B: 16 vector lanes x 16 row groups of 8; a warp owns 16 consecutive rows = one q, 16 consecutive groups
-  const int b_kg = tid & 15, b_m0 = (tid >> 4) * 8;
-  const bool b_active = !p.store_v && ((warp * 16) % MS) < nslots;
-  const int b_sw = b_kg & 7;
+  // phase F: the CTA's two halves split the rows k of the tile (8-row blocks, alternately); inside a half 8 chunk lanes x
+  // 32 row groups, a warp owns 4 MPT consecutive rows = one part, 4 MPT consecutive groups.  The halves' partial sums
+  // are added (fixed order) by phase Q.
+  const int f_half = tid >> 8, f_fg = tid & 7, f_m0 = ((tid >> 3) & 31) * MPT;
+  const bool f_active = !p.init_mode && (((warp & 7) * 4 * MPT) % MS) < nslots;
+  // phase B: lane = vector (k = lane + 32 t), warp = 8 consecutive rows = one q, 8 consecutive groups
+  const int b_m0 = warp * 8;
+  const bool b_active = !p.store_v && ((warp * 8) % MS) < nslots;
+  const int b_sw = lane & 7;
 
   float acc[8][TK];
 #pragma unroll
@@ -192,7 +197,7 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
 #pragma unroll
       for (int i = 0; i < MPT; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* ctp = CT + f_m0;
-      for (int k0 = 0; k0 < kp; k0 += 8) {
+      for (int k0 = 8 * f_half; k0 < kp; k0 += 16) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int k = k0 + u;
@@ -210,32 +215,32 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
           }
         }
       }
+      float* vdst = Vs + f_half * C::MF * FT;
 #pragma unroll
-      for (int i = 0; i < MPT; ++i) *reinterpret_cast<float4*>(Vs + (f_m0 + i) * FT + f_fg * 4) = v[i];
+      for (int i = 0; i < MPT; ++i) *reinterpret_cast<float4*>(vdst + (f_m0 + i) * FT + f_fg * 4) = v[i];
     }
     __syncthreads();
 
-    // ---------------- phase Q: lane = channel, warp w takes groups w, w + 8, ... ----------------
+    // ---------------- phase Q: lane = channel, warp w takes groups w, w + 16, ... ----------------
     {
       const int fo = j * FT + lane;
+      constexpr int QN = MS / C::NWARP;  // groups per warp
+      {
+        float in[QN][7];
+        int bl[QN];
 #pragma unroll
-      for (int h = 0; h < MS / 8; h += 4) {
-        float in[4][7];
-        int bl[4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {  // all loads of four groups first
-          const int s = warp + 8 * (h + n);
+        for (int n = 0; n < QN; ++n) {  // all loads first
+          const int s = warp + C::NWARP * n;
           bl[n] = -1;
           if (s < nslots) {
-            const ClassSlot cs = s_cs[s];
-            bl[n] = cs.bl0;
-            const size_t o = (size_t)cs.bl0 * p.nfp + fo;
+            bl[n] = s_cs[s].bl0;
+            const int o = bl[n] * p.nfp + fo;  // nbls * nfp < 2^31 is checked at plan creation
             in[n][0] = p.d_r[o];
             in[n][1] = p.d_i[o];
             in[n][2] = p.w[o];
             if (!p.init_mode && !p.store_v) {
               const int2 an = s_ant[s];
-              const size_t o0 = (size_t)an.x * p.nfp + fo, o1 = (size_t)an.y * p.nfp + fo;
+              const int o0 = an.x + fo, o1 = an.y + fo;
               in[n][3] = g_r[o0];
               in[n][4] = g_i[o0];
               in[n][5] = g_r[o1];
@@ -244,8 +249,8 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
           }
         }
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const int s = warp + 8 * (h + n);
+        for (int n = 0; n < QN; ++n) {
+          const int s = warp + C::NWARP * n;
           if (bl[n] < 0) continue;
           float qr = 0.f, qi = 0.f, pw = 0.f, qw = 0.f;
           if (p.init_mode) {  // right-hand side of the coefficient initialisation: data * (w != 0)
@@ -262,7 +267,8 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
               }
             }
           } else {
-            const float v_r = Vs[s * FT + lane], v_i = Vs[(MS + s) * FT + lane];
+            const float v_r = Vs[s * FT + lane] + Vs[(C::MF + s) * FT + lane];
+            const float v_i = Vs[(MS + s) * FT + lane] + Vs[(C::MF + MS + s) * FT + lane];
             if (p.store_v) {
               p.vout[(size_t)s_gslot[s] * p.nfp + fo] = make_float2(v_r, v_i);
               continue;
@@ -287,7 +293,7 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
                 qw += Q * w;
               }
             };
-            visibility((size_t)bl[n] * p.nfp + fo, in[n][0], in[n][1], in[n][2], in[n][3], in[n][4], in[n][5], in[n][6]);
+            visibility((size_t)(bl[n] * p.nfp + fo), in[n][0], in[n][1], in[n][2], in[n][3], in[n][4], in[n][5], in[n][6]);
             if (!SINGLE) {
               const int nb = s_cs[s].nb;
               for (int b = 1; b < nb; ++b) {
@@ -319,17 +325,19 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
 
     // ---------------- phase B ----------------
     if (b_active) {
-#pragma unroll
+#pragma unroll 2  // (fully unrolled, the 6 x TK bodies overflow the instruction cache: 'no instruction' stalls in ncu)
       for (int c4 = 0; c4 < 8; ++c4) {
         float4 q4[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q4[i] = *reinterpret_cast<const float4*>(Qs + (b_m0 + i) * FT + c4 * 4);
-        const float* ap = Ab + b_kg * FT + ((c4 ^ b_sw) << 2);
+        for (int i = 0; i < 8; ++i) q4[i] = *reinterpret_cast<const float4*>(Qs + (b_m0 + i) * FT + c4 * 4);  // warp broadcast
+        const float* ap = Ab + lane * FT + ((c4 ^ b_sw) << 2);
 #pragma unroll
         for (int t = 0; t < TK; ++t) {
-          const float4 a = *reinterpret_cast<const float4*>(ap + t * 16 * FT);
+          if (t * 32 < kp) {  // CTA-uniform: blocks of 32 vectors past the class's last row are skipped, not multiplied
+            const float4 a = *reinterpret_cast<const float4*>(ap + t * 32 * FT);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i][t] = dot4(a, q4[i], acc[i][t]);
+            for (int i = 0; i < 8; ++i) acc[i][t] = dot4(a, q4[i], acc[i][t]);
+          }
         }
       }
     }
@@ -349,7 +357,7 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
         float* dst = p.dcpart + (size_t)s_cs[s].row0 * NQ + q;
 #pragma unroll
         for (int t = 0; t < TK; ++t) {
-          const int k = b_kg + 16 * t;
+          const int k = lane + 32 * t;
           if (k < mt.ncomp) dst[(size_t)k * NQ] = acc[i][t];
         }
       }
@@ -371,7 +379,7 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
   __syncthreads();
   if (tid == 0) {
     double a = 0.0, b = 0.0, c = 0.0;
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < C::NWARP; ++w) {
       a += (double)red[w * 4 + 0];
       b += (double)red[w * 4 + 1];
       c += (double)red[w * 4 + 2];
@@ -384,24 +392,14 @@ __device__ __forceinline__ void shared_body(const SharedParams& p, const MTileDe
 }
 
 template <int MS, int NQ, bool SINGLE>
-__global__ void __launch_bounds__(256, 1) shared_kernel(const SharedParams p) {
+__global__ void __launch_bounds__(512, 1) shared_kernel(const SharedParams p) {
   extern __shared__ __align__(1024) unsigned char smem_sh[];
   const FitState* st = p.st;
   if (st->step > st->stop_after) return;  // fit already stopped (uniform across the grid)
   const MTileDesc mt = p.tiles[blockIdx.x];
-  const int tk = (mt.kp + 15) >> 4;
-  if (tk <= 2)
-    shared_body<MS, NQ, SINGLE, 2>(p, mt, smem_sh);
-  else if (tk <= 4)
-    shared_body<MS, NQ, SINGLE, 4>(p, mt, smem_sh);
-  else if (tk <= 6)
-    shared_body<MS, NQ, SINGLE, 6>(p, mt, smem_sh);
-  else if (tk <= 8)
-    shared_body<MS, NQ, SINGLE, 8>(p, mt, smem_sh);
-  else if (tk <= 10)
-    shared_body<MS, NQ, SINGLE, 10>(p, mt, smem_sh);
-  else
-    shared_body<MS, NQ, SINGLE, 13>(p, mt, smem_sh);
+  // one body for every class size: phase B skips the 32-vector blocks past kp at run time (separate TK instantiations
+  // quantised the work to {64, 128, 160, 224} rows and multiplied the code size)
+  shared_body<MS, NQ, SINGLE, SharedCfg<MS, NQ>::TKMAX>(p, mt, smem_sh);
 }
 
 }  // namespace calb2

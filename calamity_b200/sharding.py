@@ -1,8 +1,8 @@
 """Baseline-group sharding across GPUs.
 
 Every rank owns a subset of the fitting groups -- their basis rows, data, weights, coefficients and coefficient
-optimizer state -- balanced by cost (basis rows + per-baseline traffic), not by group count: every nranks-th group
-(`cyclic`, default) or a contiguous range (`contiguous`).  Gains
+optimizer state -- balanced by cost (basis rows + per-baseline traffic), not by group count: whole runs of one basis
+class (`class`, default), every nranks-th group (`cyclic`) or a contiguous range (`contiguous`).  Gains
 and their optimizer state are replicated; per iteration the ranks all-reduce the [2, nants, nfreqs] gain
 gradient and three scalars (chi^2 and the two regulariser sums).  Nothing else crosses ranks.
 """
@@ -73,17 +73,58 @@ def group_costs(layout):
     return layout.group_ncomp.astype(np.int64) * layout.group_nslots + 10 * nbl_per_group.astype(np.int64)
 
 
-def make_shard(full_layout, rank, nranks, mode="cyclic"):
-    """`cyclic` (default): rank r owns groups r, r + nranks, ... of the canonical order.  Neighbouring groups cost about
-    the same, so the ranks' loads agree to within one group, and -- unlike contiguous ranges, where a few antennas own
-    complete rows of baselines on one rank -- every antenna's baselines are spread evenly, which keeps the per-rank
-    gain-gradient reduce short and equal (measured at 8 GPUs: 35-57 us -> see profiles/).  `contiguous`: ranges of
-    near-equal cost."""
+def class_units(layout, nranks, run=64, min_members=4):
+    """Sharding units that keep the shared-basis kernel's CTAs whole: the single-slot groups of one basis class, in runs of
+    up to `run` (one CTA of calfit_shared.cuh takes up to 64 groups of one class through all channels, and skips work in
+    blocks of 8 groups -- dealing single groups round-robin would leave every rank a ragged, mostly empty CTA per class).
+    Classes too small to give every rank a full run are cut into runs of ceil(members / nranks), rounded up to 8.
+    Every other group is its own unit.  Returns a list of int64 arrays of group indices (ascending inside a unit)."""
+    cls = np.asarray(layout.group_class)
+    single = np.asarray(layout.group_nslots) == 1
+    units = []
+    by_class = {}
+    for g in range(layout.ngroups):
+        if single[g] and cls[g] >= 0:
+            by_class.setdefault(int(cls[g]), []).append(g)
+        else:
+            units.append(np.asarray([g], dtype=np.int64))
+    for members in by_class.values():
+        if len(members) < min_members:
+            units.extend(np.asarray([g], dtype=np.int64) for g in members)
+            continue
+        step = min(run, max(8, 8 * int(np.ceil(len(members) / (8.0 * nranks)))))
+        nunits = int(np.ceil(len(members) / step))
+        for u in range(nunits):  # strided: a unit's baselines come from all over the antenna list
+            units.append(np.asarray(members[u::nunits], dtype=np.int64))
+    return units
+
+
+def make_shard(full_layout, rank, nranks, mode="class"):
+    """`class` (default): whole runs of 64 groups of one basis class (see class_units) are dealt to the ranks, most expensive
+    first, each to the least loaded rank (deterministic LPT); groups without a shared basis are dealt the same way one by
+    one.  Every rank then holds whole CTAs of the shared-basis kernel, the loads agree to within one unit, and -- as with
+    `cyclic` -- every antenna's baselines end up spread over all ranks, which keeps the per-rank gain-gradient reduce
+    short.  `cyclic`: rank r owns groups r, r + nranks, ... of the canonical order (the round-1 default; right for the
+    streaming kernel).  `contiguous`: ranges of near-equal cost."""
     if nranks == 1:
         return Shard(full_layout, np.arange(full_layout.ngroups))
     if mode == "contiguous":
         g0, g1 = partition_groups(group_costs(full_layout), nranks)[rank]
         return Shard(full_layout, np.arange(g0, g1))
-    if mode != "cyclic":
+    if mode == "cyclic":
+        return Shard(full_layout, np.arange(rank, full_layout.ngroups, nranks))
+    if mode != "class":
         raise ValueError(f"unknown sharding mode {mode!r}")
-    return Shard(full_layout, np.arange(rank, full_layout.ngroups, nranks))
+    costs = group_costs(full_layout)
+    units = class_units(full_layout, nranks)
+    ucost = np.asarray([int(costs[u].sum()) for u in units], dtype=np.int64)
+    order = np.lexsort((np.asarray([int(u[0]) for u in units]), -ucost))  # cost descending, first group ascending
+    load = np.zeros(nranks, dtype=np.int64)
+    mine = []
+    for n in order:
+        r = int(np.argmin(load))  # first minimum: deterministic
+        load[r] += ucost[n]
+        if r == rank:
+            mine.append(units[n])
+    groups = np.sort(np.concatenate(mine)) if mine else np.zeros(0, np.int64)
+    return Shard(full_layout, groups)
