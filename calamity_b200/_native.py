@@ -123,6 +123,7 @@ _SIGNATURES = {
     "calb2_comm_unique_id": (C.c_int, [C.c_void_p, C.c_char_p]),
     "calb2_comm_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "calb2_comm_peer_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "calb2_comm_peer_close": (C.c_int, [C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -2,6 +2,7 @@
 // include/calamity_b200.h.  No torch types, no exceptions across the boundary.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: the ranges cost nothing unless a profiler injects itself
 
 #include <algorithm>
 #include <climits>
@@ -131,8 +132,12 @@ struct calb2_plan {
   };
   std::vector<ClsInfo> classes;
   std::vector<int> grp_cls;           // dense class index of the group, or -1: streaming path
-  std::vector<MTileDesc> mtiles[2];   // [0]: 64 groups per CTA (NQ = 2), [1]: 32 groups per CTA (NQ = 4, 'sum')
-  DevBuf<MTileDesc> d_mtiles[2];
+  // CTAs of the shared-basis kernel: [v][shape], v = 0: plain chi^2 (NQ = 2), 1: 'sum' regulariser (NQ = 4);
+  // shape 0: 256 threads, classes of <= 160 vectors, two CTAs per SM; shape 1: 512 threads, <= 208 vectors
+  std::vector<MTileDesc> mtiles[2][2];
+  DevBuf<MTileDesc> d_mtiles[2][2];
+  int nseg[2] = {1, 1};               // channel segments per class tile = planes of dcpart in use
+  long long dc_plane = 0;             // floats per plane of dcpart
   DevBuf<ClassSlot> d_cslots;
   DevBuf<int> d_cs_slot, d_slot_nb;
   long long nslots_heavy = 0, nslots_class = 0, a_class_floats = 0;
@@ -172,6 +177,8 @@ struct calb2_plan {
   void* xpeer[CALB2_MAX_RANKS] = {nullptr};
   PeerView peers{};
   unsigned int xseq = 0;  // steps enqueued so far on the exchange (identical on all ranks)
+  unsigned long long xtimeout_ns = 20000000000ull;  // bound on every wait for a peer's flag (CALB2_PEER_TIMEOUT_MS)
+  bool peers_open = false;
   DevBuf<unsigned int> tail_counter;
   // the coefficient update runs on a second stream next to the gain update (they touch disjoint state)
   cudaStream_t stream2 = nullptr;
@@ -274,22 +281,78 @@ static cudaError_t launch_heavy_f(bool sum, int qmode, const HeavyParams& hp, in
   return sum ? launch_heavy_t<FL, true, QM_GENERAL>(hp, nitems, s) : launch_heavy_t<FL, false, QM_GENERAL>(hp, nitems, s);
 }
 
-template <int MS, int NQ, bool SINGLE>
+template <int NTHR, int NQ, bool SINGLE, int KPM>
 static cudaError_t launch_shared_t(const SharedParams& sp, int ntiles, cudaStream_t s) {
-  using C = SharedCfg<MS, NQ>;
+  using C = SharedCfg<NTHR, NQ, KPM>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(shared_kernel<MS, NQ, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(shared_kernel<NTHR, NQ, SINGLE, KPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  shared_kernel<MS, NQ, SINGLE><<<ntiles, C::NTHR, C::SMEM_BYTES, s>>>(sp);
+  shared_kernel<NTHR, NQ, SINGLE, KPM><<<ntiles, NTHR, C::SMEM_BYTES, s>>>(sp);
   return cudaGetLastError();
 }
+static constexpr int KPM_SMALL = 160, KPM_LARGE = 208, SHARED_FT = 32;
+static cudaError_t launch_shared_shape(bool sum, bool single, int shape, const SharedParams& sp, int ntiles, cudaStream_t s) {
+  if (shape == 0) {
+    if (sum) return single ? launch_shared_t<256, 4, true, KPM_SMALL>(sp, ntiles, s) : launch_shared_t<256, 4, false, KPM_SMALL>(sp, ntiles, s);
+    return single ? launch_shared_t<256, 2, true, KPM_SMALL>(sp, ntiles, s) : launch_shared_t<256, 2, false, KPM_SMALL>(sp, ntiles, s);
+  }
+  if (sum) return single ? launch_shared_t<512, 4, true, KPM_LARGE>(sp, ntiles, s) : launch_shared_t<512, 4, false, KPM_LARGE>(sp, ntiles, s);
+  return single ? launch_shared_t<512, 2, true, KPM_LARGE>(sp, ntiles, s) : launch_shared_t<512, 2, false, KPM_LARGE>(sp, ntiles, s);
+}
+// groups per CTA of the four instantiations
+static int shared_ms(int v, int shape) { return (shape == 0 ? 64 : 128) / (v == 0 ? 2 : 4); }
 
 // The basis pass of one iteration: the streaming kernel over the items (groups with a private basis) and the
-// shared-basis kernel over the class tiles; both write z / dcpart / partials for their own baselines and rows.
+// shared-basis kernel over the class tiles (its large-class shape on the second stream, next to the small-class one);
+// all of them write z / dcpart / partials for their own baselines and rows.
 static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
+  const int v = sum ? 1 : 0;
+  const int n_small = (int)pl->mtiles[v][0].size(), n_large = (int)pl->mtiles[v][1].size();
+  SharedParams sp{};
+  if (n_small + n_large > 0) {
+    sp.A = hp.A;
+    sp.cslots = pl->d_cslots.p;
+    sp.cs_slot = pl->d_cs_slot.p;
+    sp.bl_ant0 = hp.bl_ant0;
+    sp.bl_ant1 = hp.bl_ant1;
+    sp.d_r = hp.d_r;
+    sp.d_i = hp.d_i;
+    sp.w = hp.w;
+    for (int b = 0; b < 2; ++b) {
+      sp.g_r[b] = hp.g_r[b];
+      sp.g_i[b] = hp.g_i[b];
+    }
+    sp.c_r = hp.c_r;
+    sp.c_i = hp.c_i;
+    sp.z = hp.z;
+    sp.y = hp.y;
+    sp.dcpart = hp.dcpart;
+    sp.dc_plane = pl->dc_plane;
+    sp.vout = hp.vout;
+    sp.st = hp.st;
+    sp.nfp = hp.nfp;
+    sp.store_v = hp.store_v;
+    sp.init_mode = hp.init_mode;
+  }
+  // the longest-running CTAs first: the large-class shape goes to the second stream before anything else is launched
+  const bool fork_large = n_large > 0 && (n_small > 0 || nitems > 0);
+  if (n_large > 0) {
+    cudaStream_t sl = s;
+    if (fork_large) {
+      cudaError_t e = cudaEventRecord(pl->ev_fork, s);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(pl->stream2, pl->ev_fork, 0);
+      if (e != cudaSuccess) return e;
+      sl = pl->stream2;
+    }
+    sp.tiles = pl->d_mtiles[v][1].p;
+    sp.partials = hp.partials + (size_t)(nitems + n_small) * 4;
+    cudaError_t e = launch_shared_shape(sum, pl->cls_single_bl, 1, sp, n_large, sl);
+    if (e == cudaSuccess && fork_large) e = cudaEventRecord(pl->ev_join, pl->stream2);
+    if (e != cudaSuccess) return e;
+  }
   if (nitems > 0) {
     const int qmode = hp.init_mode ? QM_INIT : (pl->heavy_single_bl ? QM_SINGLE : QM_GENERAL);
     cudaError_t e;
@@ -300,39 +363,19 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
     }
     if (e != cudaSuccess) return e;
   }
-  const int v = sum ? 1 : 0;
-  const int nmt = (int)pl->mtiles[v].size();
-  if (nmt == 0) return cudaSuccess;
-  SharedParams sp{};
-  sp.A = hp.A;
-  sp.tiles = pl->d_mtiles[v].p;
-  sp.cslots = pl->d_cslots.p;
-  sp.cs_slot = pl->d_cs_slot.p;
-  sp.bl_ant0 = hp.bl_ant0;
-  sp.bl_ant1 = hp.bl_ant1;
-  sp.d_r = hp.d_r;
-  sp.d_i = hp.d_i;
-  sp.w = hp.w;
-  for (int b = 0; b < 2; ++b) {
-    sp.g_r[b] = hp.g_r[b];
-    sp.g_i[b] = hp.g_i[b];
+  if (n_small > 0) {
+    sp.tiles = pl->d_mtiles[v][0].p;
+    sp.partials = hp.partials + (size_t)nitems * 4;
+    cudaError_t e = launch_shared_shape(sum, pl->cls_single_bl, 0, sp, n_small, s);
+    if (e != cudaSuccess) return e;
   }
-  sp.c_r = hp.c_r;
-  sp.c_i = hp.c_i;
-  sp.z = hp.z;
-  sp.y = hp.y;
-  sp.dcpart = hp.dcpart;
-  sp.vout = hp.vout;
-  sp.partials = hp.partials + (size_t)nitems * 4;
-  sp.st = hp.st;
-  sp.nfp = hp.nfp;
-  sp.ntiles = pl->ntiles_c;
-  sp.store_v = hp.store_v;
-  sp.init_mode = hp.init_mode;
-  if (sum) return pl->cls_single_bl ? launch_shared_t<32, 4, true>(sp, nmt, s) : launch_shared_t<32, 4, false>(sp, nmt, s);
-  return pl->cls_single_bl ? launch_shared_t<64, 2, true>(sp, nmt, s) : launch_shared_t<64, 2, false>(sp, nmt, s);
+  if (fork_large) return cudaStreamWaitEvent(s, pl->ev_join, 0);
+  return cudaSuccess;
 }
-static int n_partials(const calb2_plan* pl, bool sum) { return (int)(pl->items.size() + pl->mtiles[sum ? 1 : 0].size()); }
+static int n_partials(const calb2_plan* pl, bool sum) {
+  const int v = sum ? 1 : 0;
+  return (int)(pl->items.size() + pl->mtiles[v][0].size() + pl->mtiles[v][1].size());
+}
 
 static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, int store_v, int init_mode) {
   HeavyParams hp{};
@@ -435,6 +478,8 @@ static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitCon
   cp.k = k;
   cp.ncoef = (int)pl->ncoef;
   cp.nq = sum ? 4 : 2;
+  cp.nplanes = pl->classes.empty() ? 1 : pl->nseg[sum ? 1 : 0];
+  cp.plane = pl->dc_plane;
   cp.mode = mode;
   return cp;
 }
@@ -513,6 +558,18 @@ static int all_reduce(calb2_plan* pl, void* buf, size_t count, int dtype) {
   return 0;
 }
 
+// One payload-free round of the peer exchange on the plan's stream: publish the next sequence value, wait (bounded) for
+// every peer to publish it.  All ranks call it at the same points (fit begin, close), so it orders them.
+static int peer_barrier(calb2_plan* pl) {
+  const unsigned int seq = pl->xseq++;
+  unsigned int* my_flag = reinterpret_cast<unsigned int*>(pl->xbuf);
+  xpublish_kernel<<<1, 1, 0, pl->stream>>>(my_flag, 2u * seq + 2u);
+  CU(cudaGetLastError());
+  xwait_kernel<<<1, 32, 0, pl->stream>>>(pl->peers, 2u * seq + 2u, pl->state.p, 2, pl->xtimeout_ns);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 // One optimizer iteration (calibration.py:663-668) enqueued on the plan's stream.
 #ifdef CALB2_PROFILE
 #define CALB2_STAGE() \
@@ -525,7 +582,7 @@ static int all_reduce(calb2_plan* pl, void* buf, size_t count, int dtype) {
 static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freeze, bool want_fuse, float* hist,
                         cudaEvent_t ev0, cudaEvent_t ev1, long long* launches) {
   // coefficients can take their optimizer step in the heavy kernel's tail when nothing couples the groups
-  const bool fuse = want_fuse && !sum && !freeze && pl->all_single_slot && pl->mtiles[0].empty() &&
+  const bool fuse = want_fuse && !sum && !freeze && pl->all_single_slot && pl->classes.empty() &&
                     k.optimizer <= CALB2_OPT_SGD && k.momentum == 0.f;
   int npartials = n_partials(pl, sum);
   const double* partials = pl->partials.p;
@@ -571,6 +628,7 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
   fp.peers.n = 0;
   fp.xwait = 0;
   fp.xpar = 0;
+  fp.timeout_ns = pl->xtimeout_ns;
   dim3 ggrid(pl->nants, (pl->nfp + GK_CH - 1) / GK_CH);
   const size_t ngrad = (size_t)2 * pl->nants * pl->nfp;
   // The coefficient update only needs finalize's scalars and the fused kernel's backward sums: it is forked onto a second
@@ -639,7 +697,7 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
       CU(cudaGetLastError());
       xpublish_kernel<<<1, 1, 0, pl->stream>>>(my_flag, 2u * seq + 2u);
       CU(cudaGetLastError());
-      xwait_kernel<<<1, 32, 0, pl->stream>>>(pl->peers, 2u * seq + 2u, pl->state.p, 0);
+      xwait_kernel<<<1, 32, 0, pl->stream>>>(pl->peers, 2u * seq + 2u, pl->state.p, 1, pl->xtimeout_ns);
       CU(cudaGetLastError());
       *launches += 5;
     }
@@ -810,7 +868,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     std::vector<std::vector<int>> cands;
     for (int g = 0; g < d->ngroups; ++g) {
       const int id = d->group_class[g];
-      if (id < 0 || d->group_nslots[g] != 1 || d->group_ncomp[g] < 1 || d->group_ncomp[g] > SharedCfg<64, 2>::KPMAX) continue;
+      if (id < 0 || d->group_nslots[g] != 1 || d->group_ncomp[g] < 1 || d->group_ncomp[g] > KPM_LARGE) continue;
       auto it = index_of.find(id);
       if (it == index_of.end()) {
         it = index_of.emplace(id, (int)cands.size()).first;
@@ -865,11 +923,11 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   pl->NW = nwarp;
   pl->KMAX = nwarp * rpt * pl->G;
   {
-    const int quantum = cls_members.empty() ? pl->FT : std::max(pl->FT, SharedCfg<64, 2>::FT);
+    const int quantum = cls_members.empty() ? pl->FT : std::max(pl->FT, SHARED_FT);
     pl->nfp = ((pl->nf + quantum - 1) / quantum) * quantum;
   }
   pl->ntiles = pl->nfp / pl->FT;
-  pl->ntiles_c = pl->nfp / SharedCfg<64, 2>::FT;
+  pl->ntiles_c = pl->nfp / SHARED_FT;
   pl->grp_cls = grp_cls;
   const int G = pl->G;
 
@@ -1026,26 +1084,50 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
         rows += ci.ncomp;
         pl->n_a_nz += (long long)ci.ncomp * pl->nf;
       }
-      for (int v = 0; v < 2; ++v) {
-        const int MSv = v == 0 ? 64 : 32;
-        for (int m0 = 0; m0 < (int)mem.size(); m0 += MSv) {
-          MTileDesc mt{};
-          mt.a_off = ci.a_off;
-          mt.kp = ci.kp;
-          mt.ncomp = ci.ncomp;
-          mt.nslots = std::min(MSv, (int)mem.size() - m0);
-          mt.cs0 = first_cs + m0;
-          pl->mtiles[v].push_back(mt);
-        }
-      }
       pl->classes.push_back(ci);
+      (void)first_cs;
     }
     pl->a_class_floats = off - heavy_floats;
-    for (int v = 0; v < 2; ++v)  // longest first: cost ~ rows x (16-group blocks in use)
-      std::stable_sort(pl->mtiles[v].begin(), pl->mtiles[v].end(), [](const MTileDesc& a, const MTileDesc& b) {
-        const long long ca = (long long)a.kp * ((a.nslots + 15) / 16), cb = (long long)b.kp * ((b.nslots + 15) / 16);
-        return ca > cb;
-      });
+  }
+  {
+    // CTAs: a class is cut into tiles of MS groups; when that gives too few CTAs to balance 148 SMs (two resident CTAs
+    // each for the small shape), every tile is further cut into channel segments whose backward sums go to separate
+    // planes of dcpart and are added, in order, by coeffs_kernel.
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
+    for (int v = 0; v < 2; ++v) {
+      long long base = 0;
+      for (const auto& ci : pl->classes) base += (ci.nmembers + shared_ms(v, ci.kp <= KPM_SMALL ? 0 : 1) - 1) / shared_ms(v, ci.kp <= KPM_SMALL ? 0 : 1);
+      int nseg = 1;
+      while (nseg < 8 && nseg * 2 <= pl->ntiles_c && base * nseg < (long long)nsm * 12) nseg *= 2;
+      if (getenv("CALB2_NSEG")) nseg = std::max(1, std::min(pl->ntiles_c, atoi(getenv("CALB2_NSEG"))));
+      pl->nseg[v] = nseg;
+      int cs_cursor = 0;
+      for (const auto& ci : pl->classes) {
+        const int shape = ci.kp <= KPM_SMALL ? 0 : 1;
+        const int MSv = shared_ms(v, shape);
+        for (int m0 = 0; m0 < ci.nmembers; m0 += MSv)
+          for (int sg = 0; sg < nseg; ++sg) {
+            MTileDesc mt{};
+            mt.a_off = ci.a_off;
+            mt.kp = ci.kp;
+            mt.ncomp = ci.ncomp;
+            mt.nslots = std::min(MSv, ci.nmembers - m0);
+            mt.cs0 = cs_cursor + m0;
+            mt.j0 = (int)((long long)pl->ntiles_c * sg / nseg);
+            mt.j1 = (int)((long long)pl->ntiles_c * (sg + 1) / nseg);
+            mt.seg = sg;
+            pl->mtiles[v][shape].push_back(mt);
+          }
+        cs_cursor += ci.nmembers;
+      }
+      for (int shape = 0; shape < 2; ++shape)  // longest first: cost ~ channel tiles x rows x (8-group blocks in use)
+        std::stable_sort(pl->mtiles[v][shape].begin(), pl->mtiles[v][shape].end(), [](const MTileDesc& a, const MTileDesc& b) {
+          const long long ca = (long long)(a.j1 - a.j0) * (a.kp + 40) * ((a.nslots + 7) / 8);
+          const long long cb = (long long)(b.j1 - b.j0) * (b.kp + 40) * ((b.nslots + 7) / 8);
+          return ca > cb;
+        });
+    }
   }
   pl->slot_row0[ns] = (int)rows;
   pl->rows_total = rows;
@@ -1095,7 +1177,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
       geom[s].a_off = pl->classes[cls].a_off;
       geom[s].item_rows = pl->classes[cls].kp;
       geom[s].row_in_item = 0;
-      geom[s].swz_ft = SharedCfg<64, 2>::FT;
+      geom[s].swz_ft = SHARED_FT;
     }
     geom[s].nbls = pl->slot_nbls[s];
   }
@@ -1146,7 +1228,8 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(upload(pl->d_slot_row0, pl->slot_row0, pl));
   TRY(upload(pl->d_slot_bl0, pl->slot_bl0, pl));
   TRY(upload(pl->d_slot_nb, pl->slot_nbls, pl));
-  for (int v = 0; v < 2; ++v) TRY(upload(pl->d_mtiles[v], pl->mtiles[v], pl));
+  for (int v = 0; v < 2; ++v)
+    for (int shape = 0; shape < 2; ++shape) TRY(upload(pl->d_mtiles[v][shape], pl->mtiles[v][shape], pl));
   TRY(upload(pl->d_cslots, cslots, pl));
   TRY(upload(pl->d_cs_slot, cs_slot, pl));
   TRY(upload(pl->d_bl_ant0, pl->bl_ant0, pl));
@@ -1181,8 +1264,9 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(dalloc(pl->cu_r, (size_t)nc, pl));
   TRY(dalloc(pl->cm_i, (size_t)nc, pl));
   TRY(dalloc(pl->cu_i, (size_t)nc, pl));
-  TRY(dalloc(pl->dcpart, (size_t)rows * 4, pl));
-  TRY(dalloc(pl->partials, (pl->items.size() + std::max(pl->mtiles[0].size(), pl->mtiles[1].size())) * 4, pl));
+  pl->dc_plane = rows * 4;
+  TRY(dalloc(pl->dcpart, (size_t)pl->dc_plane * std::max(pl->nseg[0], pl->nseg[1]), pl));
+  TRY(dalloc(pl->partials, (size_t)std::max(n_partials(pl, false), n_partials(pl, true)) * 4, pl));
   TRY(dalloc(pl->red_d, 4096, pl));
   TRY(dalloc(pl->dbg_out, 16, pl));
   TRY(dalloc(pl->state, 1, pl));
@@ -1211,8 +1295,7 @@ int calb2_plan_destroy(calb2_plan* pl) {
   delete pl->gen;
   pl->gen = nullptr;
   if (pl->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(pl->comm);
-  for (int r = 0; r < CALB2_MAX_RANKS; ++r)
-    if (pl->xpeer[r]) cudaIpcCloseMemHandle(pl->xpeer[r]);
+  if (pl->peers_open) calb2_comm_peer_close(pl);
   if (pl->xbuf) cudaFree(pl->xbuf);
   DevBuf<float>* fb[] = {&pl->A, &pl->d_r, &pl->d_i, &pl->w, &pl->g_r[0], &pl->g_r[1], &pl->g_i[0], &pl->g_i[1],
                          &pl->gm_r, &pl->gu_r, &pl->gm_i, &pl->gu_i, &pl->gsnap_r, &pl->gsnap_i, &pl->ggrad_r,
@@ -1229,7 +1312,8 @@ int calb2_plan_destroy(calb2_plan* pl) {
   pl->comm_scalars.release();
   pl->light_partials.release();
   pl->d_items.release();
-  for (int v = 0; v < 2; ++v) pl->d_mtiles[v].release();
+  for (int v = 0; v < 2; ++v)
+    for (int shape = 0; shape < 2; ++shape) pl->d_mtiles[v][shape].release();
   pl->d_cslots.release();
   pl->d_cs_slot.release();
   pl->d_slot_nb.release();
@@ -1270,7 +1354,7 @@ int calb2_plan_get_info(const calb2_plan* pl, calb2_plan_info* info) {
   info->dtype = pl->dtype;
   info->n_classes = (int64_t)pl->classes.size();
   info->n_class_slots = pl->nslots_class;
-  info->n_class_ctas = (int64_t)pl->mtiles[0].size();
+  info->n_class_ctas = (int64_t)(pl->mtiles[0][0].size() + pl->mtiles[0][1].size());
   info->n_a_class = pl->a_class_floats;
   info->n_a_class_nz = 0;
   info->class_fma = 0;
@@ -1340,7 +1424,7 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* con
       jb.ncomp = ncomp;
       jb.item_rows = pl->classes[cls].kp;
       jb.row_in_item = 0;
-      jb.swz_ft = SharedCfg<64, 2>::FT;
+      jb.swz_ft = SHARED_FT;
       jobs.push_back(jb);
       pl->classes[cls].uploaded = true;
       continue;
@@ -1548,6 +1632,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, double prior_r,
   fp.peers.n = 0;
   fp.xwait = 0;
   fp.xpar = 0;
+  fp.timeout_ns = pl->xtimeout_ns;
   finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
   CU(cudaGetLastError());
   dim3 ggrid(pl->nants, (pl->nfp + GK_CH - 1) / GK_CH);
@@ -1655,6 +1740,11 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
   s0.stop_after = (int)(total - 1);
   s0.min_loss = INFINITY;
   CU(cudaMemcpyAsync(pl->state.p, &s0, sizeof(s0), cudaMemcpyHostToDevice, pl->stream));
+  // Peer exchange: every rank enters the fit through one publish / wait round.  The exchange buffers are double-buffered by
+  // the parity of the step sequence number, so the first step of this fit may only overwrite a half once every peer has
+  // finished the previous fit's last read of it -- nothing else orders the ranks between two fits.
+  if (pl->nranks > 1 && pl->peers.n > 1)
+    if (int r = peer_barrier(pl)) return r;
 
   int chunk = o->steps_per_sync > 0 ? o->steps_per_sync : 32;
   // use_graph: 1 = replay a captured graph, -1 = never, 0 = automatic: small problems are launch-latency bound (four
@@ -1685,6 +1775,7 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
     CU(cudaGraphInstantiate(&gexec, graph, 0));
   }
   CU(cudaEventRecord(ev_begin, pl->stream));
+  nvtxRangePushA("calb2_fit: step loop");
   long long done = 0;
   while (done < total) {
     const int n = (int)std::min<long long>(chunk, total - done);
@@ -1694,15 +1785,41 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
       heavy_launches += chunk;
     } else {
       for (int i = 0; i < n; ++i) {
-        if (int r = enqueue_step(pl, k, sum, freeze, o->fuse_tail_update != 0, pl->hist.p, time_heavy ? evs[2 * i] : nullptr,
-                                 time_heavy ? evs[2 * i + 1] : nullptr, &launches))
+        // the reference traces its n_profile_steps extra steps (tf.profiler.experimental.Trace, calibration.py:681-687):
+        // here they, the unrecorded warm-up step and the first recorded step get an NVTX range each (enqueue time)
+        const long long stepno = done + i;
+        const bool ranged = stepno <= (long long)o->n_profile_steps + 1;
+        if (ranged) {
+          char name[64];
+          snprintf(name, sizeof(name), stepno < o->n_profile_steps ? "calb2 profile step %lld" : (stepno == o->n_profile_steps ? "calb2 warm-up step" : "calb2 step %lld"),
+                   stepno < o->n_profile_steps ? stepno : stepno - o->n_profile_steps - 1);
+          nvtxRangePushA(name);
+        }
+        const int r = enqueue_step(pl, k, sum, freeze, o->fuse_tail_update != 0, pl->hist.p, time_heavy ? evs[2 * i] : nullptr,
+                                   time_heavy ? evs[2 * i + 1] : nullptr, &launches);
+        if (ranged) nvtxRangePop();
+        if (r) {
+          nvtxRangePop();
           return r;
+        }
         heavy_launches++;
       }
     }
     done += gexec ? chunk : n;
     CU(cudaMemcpyAsync(pl->h_state, pl->state.p, sizeof(FitState), cudaMemcpyDeviceToHost, pl->stream));
     CU(cudaStreamSynchronize(pl->stream));
+    if (pl->h_state->error) {
+      nvtxRangePop();
+      cudaEventDestroy(ev_begin);
+      cudaEventDestroy(ev_end);
+      for (auto& e : evs) cudaEventDestroy(e);
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (graph) cudaGraphDestroy(graph);
+      return fail(CALB2_ERR_TIMEOUT, "peer exchange timed out after %.1f s waiting for rank %d at step %d (rank %d of %d): the "
+                  "ranks must call calb2_fit with identical maxsteps / tol / n_profile_steps / steps_per_sync, and a rank that "
+                  "failed must not leave the others waiting", pl->xtimeout_ns * 1e-9, pl->h_state->error_rank, pl->h_state->step,
+                  pl->rank, pl->nranks);
+    }
     const bool stopped = pl->h_state->step > pl->h_state->stop_after;
     if (time_heavy) {
         for (int i = 0; i < n; ++i) {  // kernels past the stop are no-ops with ~zero duration
@@ -1715,6 +1832,7 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
   }
   CU(cudaEventRecord(ev_end, pl->stream));
   CU(cudaStreamSynchronize(pl->stream));
+  nvtxRangePop();
   float loop_ms = 0.f;
   CU(cudaEventElapsedTime(&loop_ms, ev_begin, ev_end));
   const FitState hs = *pl->h_state;
@@ -1856,11 +1974,43 @@ int calb2_comm_peer_import(calb2_plan* pl, const void* ipc_handles, int32_t rank
     pl->peers.grad[r] = reinterpret_cast<const float*>(base + ngrad_off);
   }
   pl->xseq = 0;
+  pl->peers_open = true;
+  if (const char* t = getenv("CALB2_PEER_TIMEOUT_MS")) pl->xtimeout_ns = (unsigned long long)std::max(1.0, atof(t)) * 1000000ull;
   if (!pl->tail_counter.p) {
     CU(pl->tail_counter.alloc(1));
     CU(cudaMemset(pl->tail_counter.p, 0, sizeof(unsigned int)));
   }
   return 0;
+}
+
+int calb2_comm_peer_close(calb2_plan* pl) {
+  if (!pl) return fail(CALB2_ERR_ARG, "null argument");
+  if (!pl->peers_open) return 0;
+  CU(cudaSetDevice(pl->device));
+  // one last round: nobody unmaps (and the owner does not free) a buffer while a peer may still be reading it in its
+  // own last step; a peer that is gone only costs the time-out
+  int rc = 0;
+  if (pl->peers.n > 1 && pl->state.p) {
+    FitState s{};
+    CU(cudaMemcpyAsync(pl->state.p, &s, sizeof(s), cudaMemcpyHostToDevice, pl->stream));
+    rc = peer_barrier(pl);
+    if (!rc) {
+      CU(cudaMemcpyAsync(pl->h_state, pl->state.p, sizeof(FitState), cudaMemcpyDeviceToHost, pl->stream));
+      CU(cudaStreamSynchronize(pl->stream));
+      if (pl->h_state->error)
+        rc = fail(CALB2_ERR_TIMEOUT, "peer exchange close: rank %d did not arrive within %.1f s", pl->h_state->error_rank,
+                  pl->xtimeout_ns * 1e-9);
+    }
+  }
+  for (int r = 0; r < CALB2_MAX_RANKS; ++r)
+    if (pl->xpeer[r]) {
+      cudaIpcCloseMemHandle(pl->xpeer[r]);
+      pl->xpeer[r] = nullptr;
+    }
+  pl->peers_open = false;
+  pl->peers.n = 0;
+  pl->nranks = 1;
+  return rc;
 }
 
 }  // extern "C"

@@ -48,6 +48,8 @@ struct FitState {
   double m_schedule; // Nadam: running product of the momentum schedule (Keras `_m_cache`)
   float s_r, s_i;
   double chi2;
+  int error;         // 1: a peer did not publish its partials within the exchange time-out (the fit was aborted)
+  int error_rank;    // the first rank that was late
 };
 
 struct FitConsts {
@@ -91,17 +93,41 @@ __global__ void xpublish_kernel(unsigned int* flag, unsigned int value) {
   __threadfence_system();
   st_release_sys(flag, value);
 }
-// one lane per rank waits until that rank has published step `value`
-__device__ __forceinline__ void xwait_all(const PeerView& pv, unsigned int value) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// One lane per rank waits until that rank has published step `value` -- but never longer than `timeout_ns` (a peer that
+// died, diverged or was given different loop parameters would otherwise hang every other GPU of the node for good).
+// Returns -1 when every flag arrived, else the first late rank (identical in every thread of the CTA).
+__device__ __forceinline__ int xwait_all(const PeerView& pv, unsigned int value, unsigned long long timeout_ns) {
+  __shared__ int s_late;
+  if (threadIdx.x == 0) s_late = 0x7fffffff;
+  __syncthreads();
   if ((int)threadIdx.x < pv.n) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
     while ((int)(ld_acquire_sys(pv.flag[threadIdx.x]) - value) < 0) {
+      if ((++spins & 1023u) == 0u && global_timer_ns() - t0 > timeout_ns) {
+        atomicMin(&s_late, (int)threadIdx.x);
+        break;
+      }
     }
   }
   __syncthreads();
+  return s_late == 0x7fffffff ? -1 : s_late;
 }
-__global__ void xwait_kernel(const PeerView pv, unsigned int value, const FitState* st, int before_finalize) {
-  if (before_finalize ? (st->step > st->stop_after) : !st->upd_active) return;
-  xwait_all(pv, value);
+// after_update: 0 = wait before this step's finalize, 1 = wait before its gain update, 2 = unconditional (fit begin / close)
+__global__ void xwait_kernel(const PeerView pv, unsigned int value, FitState* st, int mode, unsigned long long timeout_ns) {
+  if (mode == 0 ? (st->step > st->stop_after) : (mode == 1 ? !st->upd_active : false)) return;
+  const int late = xwait_all(pv, value, timeout_ns);
+  if (late >= 0 && threadIdx.x == 0) {  // abort: nothing after this point may use the peers' partials
+    st->error = 1;
+    st->error_rank = late;
+    st->upd_active = 0;
+    st->stop_after = st->step - 1;
+  }
 }
 
 struct HeavyParams {
@@ -800,6 +826,7 @@ struct FinalizeParams {
   PeerView peers; // peers.n > 1: wait until every rank's flag reached `xwait`, then add their scalars in rank order
   unsigned int xwait;
   int xpar;       // parity of the step sequence number (selects the half of the double-buffered partials)
+  unsigned long long timeout_ns;  // bound on the wait for the peers' flags
 };
 
 __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams p) {
@@ -811,8 +838,15 @@ __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams 
   }
   double a = 0.0, b = 0.0, c = 0.0;
   if (p.peers.n > 1) {
-    xwait_all(p.peers, p.xwait);
+    const int late = xwait_all(p.peers, p.xwait, p.timeout_ns);
     if (threadIdx.x != 0) return;
+    if (late >= 0) {  // a peer never published: abort the fit instead of spinning (the host reports CALB2_ERR_TIMEOUT)
+      st->error = 1;
+      st->error_rank = late;
+      st->upd_active = 0;
+      st->stop_after = st->step - 1;
+      return;
+    }
     const int par = p.xpar;
     for (int r = 0; r < p.peers.n; ++r) {  // rank order: identical sums on every rank
       const volatile double* sc = p.peers.scal[r] + par * 4;
@@ -1225,6 +1259,8 @@ struct CoeffParams {
   FitConsts k;
   int ncoef;
   int nq;
+  int nplanes;    // planes of dcpart to add (channel segments of the shared-basis kernel; the streaming kernel writes plane 0)
+  long long plane;  // floats per plane
   int mode;       // 0: update; 1: gradient only; 3: snapshot copy only (freeze_model)
 };
 
@@ -1250,6 +1286,15 @@ __global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
     if (p.nq == 4) {
       t2 = d[2];
       t3 = d[3];
+    }
+    for (int pn = 1; pn < p.nplanes; ++pn) {  // channel segments, fixed order
+      d += p.plane;
+      t0 += d[0];
+      t1 += d[1];
+      if (p.nq == 4) {
+        t2 += d[2];
+        t3 += d[3];
+      }
     }
   }
   if (ns > 1) {

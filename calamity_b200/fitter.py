@@ -199,6 +199,9 @@ class FitPlan:
         assert len(blob) == 64 * nranks, len(blob)
         buf = (C.c_char * len(blob)).from_buffer_copy(blob)
         nat.check(self._lib.calb2_comm_peer_import(self._handle, C.cast(buf, C.c_void_p), rank, nranks))
+    def peer_close(self):
+        """Last publish / wait round of the exchange, then unmap the peers' buffers (every rank must call it)."""
+        nat.check(self._lib.calb2_comm_peer_close(self._handle))
 
 
 def comm_init_peer(plan, rank, world):

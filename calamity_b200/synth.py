@@ -141,6 +141,9 @@ CONFIGS = {
     "hera37": dict(nants=37, nfreqs=384),
     "hera128": dict(nants=128, nfreqs=1024),
     "hera350": dict(nants=350, nfreqs=1024),
+    # the one configuration the reference publishes a number for (examples/Calamity_Tutorial.ipynb:1178): 15 antennas,
+    # 105 baselines x 200 channels
+    "tutorial15": dict(nants=15, nfreqs=200, df=100e3),
 }
 
 

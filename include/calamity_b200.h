@@ -45,7 +45,8 @@ enum {
   CALB2_ERR_UNSUPPORTED = -3,
   CALB2_ERR_STATE = -4,    /* call order violated (e.g. fit before set_integration) */
   CALB2_ERR_NCCL = -5,
-  CALB2_ERR_NONFINITE = -6
+  CALB2_ERR_NONFINITE = -6,
+  CALB2_ERR_TIMEOUT = -7   /* peer exchange: a rank did not publish its partial sums in time (fit aborted on every rank) */
 };
 
 /* tf.optimizers.* of calibration.py:17-27 that have a device implementation (all but tensorflow-addons' LAMB). */
@@ -202,10 +203,14 @@ int calb2_comm_unique_id(void* nccl_unique_id_out, const char* nccl_lib);
  * rank.  Per iteration a rank writes its partial sums / gain-gradient partial into its own buffer and raises a flag;
  * the finalize and gain-update kernels read all ranks' partials over NVLink and add them in rank order, so the
  * reduction is fused into the consumers, deterministic and bit-identical on all ranks.  One node, <= 16 ranks.
- * Lifetime: the peers read a rank's buffer during their own last step, so a plan must not be destroyed before every
- * rank has returned from its last calb2_fit (synchronise the ranks before calb2_plan_destroy). */
+ * Every wait on a peer is bounded (20 s, environment CALB2_PEER_TIMEOUT_MS): a rank that died, or was given different
+ * maxsteps / tol / n_profile_steps / steps_per_sync, makes calb2_fit return CALB2_ERR_TIMEOUT on the others instead of
+ * hanging their GPUs.  calb2_fit starts with one publish / wait round, so consecutive fits cannot overrun each other's
+ * buffers.  Lifetime: calb2_comm_peer_close (called by calb2_plan_destroy if the caller did not) runs one last round
+ * before it unmaps the peers' buffers, so no rank frees a buffer a peer is still reading; every rank must call it. */
 int calb2_comm_peer_export(calb2_plan* plan, void* ipc_handle_out);
 int calb2_comm_peer_import(calb2_plan* plan, const void* ipc_handles, int32_t rank, int32_t nranks);
+int calb2_comm_peer_close(calb2_plan* plan);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ def main():
     workload = sys.argv[1] if len(sys.argv) > 1 else "hera37"
     reg = sys.argv[2] if len(sys.argv) > 2 else "none"
     comm = sys.argv[3] if len(sys.argv) > 3 else "peer"
+    scenario = sys.argv[4] if len(sys.argv) > 4 else "parity"
     prob = synth.make(workload, init_gain_scatter=0.02, coeff_error=0.05)
     full = prob.layout()
     shard = make_shard(full, rank, world)
@@ -51,11 +52,31 @@ def main():
     pi = float(np.sum(prob.data_i.astype(np.float64) * prob.wgts))
     kw = dict(optimizer="Adamax", maxsteps=40, tol=0.0, learning_rate=1e-2, model_regularization=None if reg == "none" else "sum",
               prior_r_sum=pr, prior_i_sum=pi)
+    if scenario == "timeout":
+        # rank 1 asks for fewer steps than rank 0: rank 0 must come back with CALB2_ERR_TIMEOUT (-7), not hang its GPU
+        from calamity_b200._native import NativeError
+
+        kw["maxsteps"] = 40 if rank == 0 else 8
+        t0 = __import__("time").perf_counter()
+        try:
+            plan.fit(**kw)
+            outcome = "returned"
+        except NativeError as e:
+            outcome = "timeout" if "(-7)" in str(e) else f"other error: {e}"
+        dt = __import__("time").perf_counter() - t0
+        log("fit", outcome, f"{dt:.1f} s")
+        plan.close()
+        want = "timeout" if rank == 0 else "returned"
+        ok = outcome == want and dt < 30.0
+        print(f"{'PASS' if ok else 'FAIL'} rank {rank} scenario=timeout outcome={outcome} ({dt:.1f} s)", flush=True)
+        res = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(res, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        sys.exit(0 if int(res.item()) == 1 else 1)
     hist, res = plan.fit(**kw)
     g_r, g_i = plan.get_gains()
     torch.cuda.synchronize()
-    dist.barrier()  # peers read this rank's exchange buffer in their last step: nobody frees it before all are done
-    plan.close()
+    plan.close()  # runs the exchange's last publish / wait round: no rank unmaps a buffer a peer still reads
     log("sharded fit done", hist[:2], hist[-1])
     ok = True
     if rank == 0:

@@ -175,7 +175,9 @@ def test_calibrate_and_model_dpss_freeze_model(sky):
     assert np.allclose(model.data_array, sky_model.data_array, atol=1e-5 * fx.rms(model.data_array))
     assert np.allclose(np.abs(gains_out.gain_array), 1.0, rtol=0.0, atol=2e-2)  # fitted towards the true unity gains
     assert len(hist) == 1 and len(hist[0]) == 1
-    assert gains_in is not gains_out or True
+    # the fit moved the gains away from their perturbed starting values (the driver writes into the UVCal it was given,
+    # calibration.py:1294-1300; gains_in is the untouched copy)
+    assert gains_out is gains and not np.allclose(gains_out.gain_array, gains_in.gain_array)
 
 
 @pytest.mark.parametrize("n_profile_steps, model_regularization", [(10, "post_hoc"), (0, "sum")])

@@ -115,7 +115,11 @@ def test_other_keras_optimizers(native_built, optimizer, opt_kw):
     # (Ftrl rebuilds the parameters from its accumulators, so with non-zero initial values the first steps pull them
     # to ~0 and the loss rises to ~1 -- in TensorFlow as here; only finiteness is asserted for it)
     assert np.all(np.isfinite(hist)) and (optimizer == "Ftrl" or ref[-1] < ref[0])
-    assert err.max() < 1e-5
+    # 1e-5 (BASELINE.json), or twice the distance of the float32 NumPy restatement to the same float64 yardstick where that
+    # is larger: Nadam drops the loss 170-fold in 40 steps, and there the float32 restatement itself is 1.6e-5 away
+    # (two correct float32 implementations differ once the loss is rounding-dominated)
+    err32 = np.abs(np.asarray(o32[4]["loss"], dtype=np.float64) - ref) / ref
+    assert err.max() < max(1e-5, 2.0 * err32.max()), (err.max(), err32.max())
     lay = t64["lay"]
     # Rules that divide by sqrt(mean g^2) (RMSprop, Adadelta, Ftrl) turn rounding noise on near-zero gradient entries
     # into O(lr) parameter differences in ANY float32 implementation: the bound is 1e-4 or three times the distance of
