@@ -57,6 +57,27 @@ def _device_index():
     return int(os.environ.get("CALAMITY_B200_DEVICE", "0"))
 
 
+def _device_indices(nunits, sequential):
+    """CUDA devices the driver spreads its independent (polarization, time) integrations over (calibration.py:1160-1167:
+    the units share the basis and nothing else, unless init_guesses_from_previous_time_step chains them, calibration.py:1210).
+    CALAMITY_B200_DEVICES = "all" (default) | "0,2,3"; CALAMITY_B200_DEVICE (or the file driver's gpu_index) pins one
+    device, like the reference's `gpu_index` (calibration.py:1741-1752).  Never more devices than units."""
+    if sequential or nunits < 2 or "CALAMITY_B200_DEVICE" in os.environ:
+        return [_device_index()]
+    spec = os.environ.get("CALAMITY_B200_DEVICES", "all").strip()
+    if spec == "all":
+        import ctypes
+
+        from . import _native as nat
+
+        n = ctypes.c_int32(0)
+        nat.check(nat.load().calb2_device_count(ctypes.byref(n)))
+        devs = list(range(max(1, n.value)))
+    else:
+        devs = [int(x) for x in spec.split(",") if x.strip() != ""]
+    return devs[: max(1, min(len(devs), nunits))] or [0]
+
+
 # ----------------------------------------------------------------------------------------------------
 # marshalling (calibration.py:30-444)
 # ----------------------------------------------------------------------------------------------------
@@ -591,68 +612,96 @@ def calibrate_and_model_tensor(
                             nants=max(len(ants_map), uvdata.Nants_data), dtype=fdt)
     bl_pairs = list(zip(lay.bl_ant0.tolist(), lay.bl_ant1.tolist()))
     del fg_model_comps_dict
-    plan = FitPlan(lay, device=_device_index())
+    pols = list(uvdata.get_pols())
+    times = list(np.unique(uvdata.time_array))
+    devices = _device_indices(len(pols) * len(times), init_guesses_from_previous_time_step)
+    plans = [FitPlan(lay, device=d) for d in devices]  # the basis is replicated: one upload per device, once per call
     echo(f"{datetime.datetime.now()}Finished Converting Foreground Modeling Components to Tensors...\n", verbose=verbose)
+    state = {}  # (plan index) -> carried (g_r, g_i, first_time) for init_guesses_from_previous_time_step
+
+    def process(plan, pidx, polnum, pol, time_index, time):
+        """One (polarization, time) integration on `plan` (calibration.py:1167-1320).  Units write disjoint slices of
+        model / gains / resid, so several of them may run on different devices at once."""
+        echo(f"{datetime.datetime.now()} Working on pol {pol}, {polnum + 1} of {uvdata.Npols}, time {time_index + 1} of "
+             f"{uvdata.Ntimes}...\n", verbose=verbose)
+        bltsel = np.isclose(uvdata.time_array, time, atol=1e-7, rtol=0.0)
+        unflagged = ~uvdata.flag_array[bltsel, 0, :, polnum]
+        frac_unflagged = np.count_nonzero(unflagged) / (uvdata.Nbls * uvdata.Nfreqs)
+        history = None
+        if frac_unflagged >= skip_threshold:
+            rmsdata = np.sqrt(np.mean(np.abs(uvdata.data_array[bltsel, 0, :, polnum][unflagged]) ** 2.0))
+            echo(f"{datetime.datetime.now()} Tensorizing data...\n", verbose=verbose)
+            d_r, d_i, w = _tensorize_data_flat(uvdata, bl_pairs, ants_map, pol, time, rmsdata, weights,
+                                               nsamples_in_weights, fdt)
+            plan.set_integration(d_r, d_i, w)
+            s_r = s_i = None
+            if sky_model is not None:
+                echo(f"{datetime.datetime.now()} Tensorizing sky model...\n", verbose=verbose)
+                s_r, s_i, _ = _tensorize_data_flat(sky_model, bl_pairs, ants_map, pol, time, rmsdata, weights,
+                                                   False, fdt)
+            carried = state.get((pidx, polnum))
+            if carried is None or not init_guesses_from_previous_time_step:
+                echo(f"{datetime.datetime.now()} Tensorizing Gains...\n", verbose=verbose)
+                g_r, g_i = tensorize_gains(gains, dtype=fdt, time=time, polarization=pol)
+                g_r, g_i = _pad_gain_rows(g_r, lay.nants), _pad_gain_rows(g_i, lay.nants, fill=0.0)
+                plan.set_gains(g_r, g_i)
+                echo(f"{datetime.datetime.now()} Tensorizing Foreground coeffs...\n", verbose=verbose)
+                plan.init_coeffs(s_r, s_i)  # TypeError on a None sky model, like tensorize_fg_coeffs(None, ...)
+                if use_model_snr_weights:
+                    plan.apply_model_snr_weights()
+            else:
+                g_r, g_i = carried
+            priors = (0.0, 0.0)
+            if model_regularization == "sum":
+                priors = plan.prior_sums(s_r, s_i)
+            out = _run_fit(plan, lay, g_r, g_i, None, None, use_min, tol, maxsteps, optimizer, freeze_model,
+                           verbose, n_profile_steps, profile_log_dir, model_regularization, priors, dtype,
+                           opt_kwargs, graph_mode=graph_mode)
+            g_r, g_i, _, _, history = out
+            state[(pidx, polnum)] = (g_r, g_i)
+            vis_r, vis_i = plan.get_model()
+            cube_r = np.zeros((lay.nants, lay.nants, lay.nfreqs))
+            cube_i = np.zeros_like(cube_r)
+            cube_r[lay.bl_ant0, lay.bl_ant1] = vis_r
+            cube_i[lay.bl_ant0, lay.bl_ant1] = vis_i
+            insert_model_into_uvdata_tensor(uvdata=model, time=time, polarization=pol, ants_map=ants_map,
+                                            red_grps=red_grps, model_r=cube_r, model_i=cube_i,
+                                            scale_factor=rmsdata)
+            insert_gains_into_uvcal(uvcal=gains, time=time, polarization=pol, gains_re=g_r, gains_im=g_i)
+        else:
+            echo(f"{datetime.datetime.now()}: Only {frac_unflagged * 100}-percent of data unflagged. Skipping...\n",
+                 verbose=verbose)
+            flag_poltime(resid, time=time, polarization=pol)
+            flag_poltime(gains, time=time, polarization=pol)
+            flag_poltime(model, time=time, polarization=pol)
+        if not freeze_model and model_regularization == "post_hoc" and np.any(~model.flag_array[bltsel]):
+            renormalize(uvdata_reference_model=sky_model, uvdata_deconv=model, gains=gains, polarization=pol,
+                        time=time, additional_flags=uvdata.flag_array)
+        return history
+
+    units = [(polnum, pol, ti, t) for polnum, pol in enumerate(pols) for ti, t in enumerate(times)]
+    results = {}
     try:
-        for polnum, pol in enumerate(uvdata.get_pols()):
-            echo(f"{datetime.datetime.now()} Working on pol {pol}, {polnum + 1} of {uvdata.Npols}...\n", verbose=verbose)
-            fit_history_p = {}
-            first_time = True
-            for time_index, time in enumerate(np.unique(uvdata.time_array)):
-                echo(f"{datetime.datetime.now()} Working on time {time_index + 1} of {uvdata.Ntimes}...\n", verbose=verbose)
-                bltsel = np.isclose(uvdata.time_array, time, atol=1e-7, rtol=0.0)
-                unflagged = ~uvdata.flag_array[bltsel, 0, :, polnum]
-                frac_unflagged = np.count_nonzero(unflagged) / (uvdata.Nbls * uvdata.Nfreqs)
-                if frac_unflagged >= skip_threshold:
-                    rmsdata = np.sqrt(np.mean(np.abs(uvdata.data_array[bltsel, 0, :, polnum][unflagged]) ** 2.0))
-                    echo(f"{datetime.datetime.now()} Tensorizing data...\n", verbose=verbose)
-                    d_r, d_i, w = _tensorize_data_flat(uvdata, bl_pairs, ants_map, pol, time, rmsdata, weights,
-                                                       nsamples_in_weights, fdt)
-                    plan.set_integration(d_r, d_i, w)
-                    s_r = s_i = None
-                    if sky_model is not None:
-                        echo(f"{datetime.datetime.now()} Tensorizing sky model...\n", verbose=verbose)
-                        s_r, s_i, _ = _tensorize_data_flat(sky_model, bl_pairs, ants_map, pol, time, rmsdata, weights,
-                                                           False, fdt)
-                    if first_time or not init_guesses_from_previous_time_step:
-                        first_time = False
-                        echo(f"{datetime.datetime.now()} Tensorizing Gains...\n", verbose=verbose)
-                        g_r, g_i = tensorize_gains(gains, dtype=fdt, time=time, polarization=pol)
-                        g_r, g_i = _pad_gain_rows(g_r, lay.nants), _pad_gain_rows(g_i, lay.nants, fill=0.0)
-                        plan.set_gains(g_r, g_i)
-                        echo(f"{datetime.datetime.now()} Tensorizing Foreground coeffs...\n", verbose=verbose)
-                        plan.init_coeffs(s_r, s_i)  # TypeError on a None sky model, like tensorize_fg_coeffs(None, ...)
-                        if use_model_snr_weights:
-                            plan.apply_model_snr_weights()
-                    priors = (0.0, 0.0)
-                    if model_regularization == "sum":
-                        priors = plan.prior_sums(s_r, s_i)
-                    out = _run_fit(plan, lay, g_r, g_i, None, None, use_min, tol, maxsteps, optimizer, freeze_model,
-                                   verbose, n_profile_steps, profile_log_dir, model_regularization, priors, dtype,
-                                   opt_kwargs, graph_mode=graph_mode)
-                    g_r, g_i, _, _, fit_history_p[time_index] = out
-                    vis_r, vis_i = plan.get_model()
-                    cube_r = np.zeros((lay.nants, lay.nants, lay.nfreqs))
-                    cube_i = np.zeros_like(cube_r)
-                    cube_r[lay.bl_ant0, lay.bl_ant1] = vis_r
-                    cube_i[lay.bl_ant0, lay.bl_ant1] = vis_i
-                    insert_model_into_uvdata_tensor(uvdata=model, time=time, polarization=pol, ants_map=ants_map,
-                                                    red_grps=red_grps, model_r=cube_r, model_i=cube_i,
-                                                    scale_factor=rmsdata)
-                    insert_gains_into_uvcal(uvcal=gains, time=time, polarization=pol, gains_re=g_r, gains_im=g_i)
-                else:
-                    echo(f"{datetime.datetime.now()}: Only {frac_unflagged * 100}-percent of data unflagged. Skipping...\n",
-                         verbose=verbose)
-                    flag_poltime(resid, time=time, polarization=pol)
-                    flag_poltime(gains, time=time, polarization=pol)
-                    flag_poltime(model, time=time, polarization=pol)
-                    fit_history[polnum] = "skipped!"
-                if not freeze_model and model_regularization == "post_hoc" and np.any(~model.flag_array[bltsel]):
-                    renormalize(uvdata_reference_model=sky_model, uvdata_deconv=model, gains=gains, polarization=pol,
-                                time=time, additional_flags=uvdata.flag_array)
-            fit_history[polnum] = fit_history_p
+        if len(plans) == 1:
+            for (polnum, pol, ti, t) in units:
+                results[(polnum, ti)] = process(plans[0], 0, polnum, pol, ti, t)
+        else:
+            # one host thread per device (ctypes releases the GIL during native calls; a plan is driven by one thread at a
+            # time, include/calamity_b200.h), units dealt round-robin, no communication between devices
+            from concurrent.futures import ThreadPoolExecutor
+
+            def worker(k):
+                return {(u[0], u[2]): process(plans[k], k, *u) for u in units[k :: len(plans)]}
+
+            with ThreadPoolExecutor(max_workers=len(plans)) as pool:
+                for part in pool.map(worker, range(len(plans))):
+                    results.update(part)
     finally:
-        plan.close()
+        for plan in plans:
+            plan.close()
+    for polnum, _ in enumerate(pols):
+        # skipped units leave no entry (the reference overwrites its "skipped!" marker the same way, quirk Q10)
+        fit_history[polnum] = {ti: results[(polnum, ti)] for ti, _ in enumerate(times) if results.get((polnum, ti)) is not None}
 
     model_with_gains = cal_utils.apply_gains(model, gains, inverse=True)
     if not correct_model:

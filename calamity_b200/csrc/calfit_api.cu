@@ -138,6 +138,7 @@ struct calb2_plan {
   DevBuf<MTileDesc> d_mtiles[2][2];
   int nseg[2] = {1, 1};               // channel segments per class tile = planes of dcpart in use
   long long dc_plane = 0;             // floats per plane of dcpart
+  int first_class_row = 0;            // rows below it belong to the streaming path (plane 0 only)
   DevBuf<ClassSlot> d_cslots;
   DevBuf<int> d_cs_slot, d_slot_nb;
   long long nslots_heavy = 0, nslots_class = 0, a_class_floats = 0;
@@ -258,16 +259,24 @@ static int choose_fl(const calb2_plan_desc* d, int RPT, int NWARP, int* fl_out) 
   return fail(CALB2_ERR_UNSUPPORTED, "a group has %d basis vectors; at most %d are supported", maxc, NWARP * RPT * 8);
 }
 
+static constexpr int MAX_DEVICES = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < MAX_DEVICES ? dev : 0;
+}
+
 template <int FL, bool SUM, int QMODE>
 static cudaError_t launch_heavy_t(const HeavyParams& hp, int nitems, cudaStream_t s) {
   constexpr int RPT = RPT_DEFAULT, MINB = CALB2_MINB;
   using C = HeavyCfg<FL, SUM, RPT>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[MAX_DEVICES] = {};  // the attribute is per device (the driver runs one plan per GPU)
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(heavy_kernel<FL, SUM, RPT, MINB, QMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   heavy_kernel<FL, SUM, RPT, MINB, QMODE><<<nitems, C::NTHR, C::SMEM_BYTES, s>>>(hp);
   return cudaGetLastError();
@@ -284,11 +293,12 @@ static cudaError_t launch_heavy_f(bool sum, int qmode, const HeavyParams& hp, in
 template <int NTHR, int NQ, bool SINGLE, int KPM>
 static cudaError_t launch_shared_t(const SharedParams& sp, int ntiles, cudaStream_t s) {
   using C = SharedCfg<NTHR, NQ, KPM>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(shared_kernel<NTHR, NQ, SINGLE, KPM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   shared_kernel<NTHR, NQ, SINGLE, KPM><<<ntiles, NTHR, C::SMEM_BYTES, s>>>(sp);
   return cudaGetLastError();
@@ -480,6 +490,7 @@ static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitCon
   cp.nq = sum ? 4 : 2;
   cp.nplanes = pl->classes.empty() ? 1 : pl->nseg[sum ? 1 : 0];
   cp.plane = pl->dc_plane;
+  cp.first_class_row = pl->first_class_row;
   cp.mode = mode;
   return cp;
 }
@@ -792,10 +803,11 @@ static int init_coeffs_impl(calb2_plan* pl, const float* sky_r, const float* sky
     CU(cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(GramJob), cudaMemcpyHostToDevice, pl->stream));
     constexpr int FC = 32;
     const size_t smem = (size_t)maxn * (FC + 1) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (smem > configured[dev]) {
       CU(cudaFuncSetAttribute(gram_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 << 10)));
-      configured = smem;
+      configured[dev] = smem;
     }
     gram_kernel<FC><<<(unsigned)jobs.size(), 256, smem, pl->stream>>>(pl->A.p, djobs.p, pl->slot_geom.p, gram.p, pl->nf, pl->FT);
     CU(cudaGetLastError());
@@ -844,7 +856,15 @@ static int init_coeffs_impl(calb2_plan* pl, const float* sky_r, const float* sky
 extern "C" {
 
 const char* calb2_last_error(void) { return g_err.c_str(); }
-const char* calb2_version(void) { return "calamity_b200 0.1 (sm_100a)"; }
+const char* calb2_version(void) { return "calamity_b200 0.2 (sm_100a)"; }
+
+int calb2_device_count(int32_t* count) {
+  if (!count) return fail(CALB2_ERR_ARG, "null argument");
+  int n = 0;
+  CU(cudaGetDeviceCount(&n));
+  *count = n;
+  return 0;
+}
 
 int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   if (!d || !out) return fail(CALB2_ERR_ARG, "null argument");
@@ -1055,6 +1075,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     for (long long s = 0; s < nh; ++s) pl->slot_item[s] = new_index[pl->slot_item[s]];
   }
   const long long heavy_rows = rows;
+  pl->first_class_row = (int)heavy_rows;
   const long long heavy_floats = heavy_rows * (long long)pl->nfp;
 
   // ---- shared-basis path: one block per class after the streaming tiles; backward-sum rows after the streaming rows ----

@@ -405,7 +405,7 @@ template <int FL, bool SUM, int RPT, int MINB, int QMODE>
 __global__ void __launch_bounds__(256, MINB) heavy_kernel(const HeavyParams p) {
   using C = HeavyCfg<FL, SUM, RPT>;
   constexpr int G = C::G, FT = C::FT, NQ = C::NQ;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
 
   const FitState* st = p.st;
   if (st->step > st->stop_after) return;  // fit already stopped (uniform across the grid)
@@ -1259,7 +1259,9 @@ struct CoeffParams {
   FitConsts k;
   int ncoef;
   int nq;
-  int nplanes;    // planes of dcpart to add (channel segments of the shared-basis kernel; the streaming kernel writes plane 0)
+  int nplanes;    // planes of dcpart to add for rows >= first_class_row (channel segments of the shared-basis kernel);
+                  // the streaming kernel's rows live in plane 0 only -- the other planes hold other layouts' data there
+  int first_class_row;
   long long plane;  // floats per plane
   int mode;       // 0: update; 1: gradient only; 3: snapshot copy only (freeze_model)
 };
@@ -1287,7 +1289,8 @@ __global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
       t2 = d[2];
       t3 = d[3];
     }
-    for (int pn = 1; pn < p.nplanes; ++pn) {  // channel segments, fixed order
+    const int np = p.coef_row0[c] >= p.first_class_row ? p.nplanes : 1;
+    for (int pn = 1; pn < np; ++pn) {  // channel segments, fixed order
       d += p.plane;
       t0 += d[0];
       t1 += d[1];

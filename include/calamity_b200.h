@@ -150,6 +150,10 @@ typedef struct {
 
 const char* calb2_last_error(void);
 const char* calb2_version(void);
+/* Number of CUDA devices visible to the process.  The reference's only device logic is "make one GPU visible"
+ * (calibration.py:1741-1752, 1796-1800); the drop-in driver spreads the independent (polarization, time) integrations of
+ * calibration.py:1160-1167 over all of them, one plan per device. */
+int calb2_device_count(int32_t* count);
 
 /* Once per calibrate_and_model_tensor call: mirrors calibration.py:1143-1152. */
 int calb2_plan_create(const calb2_plan_desc* desc, calb2_plan** out);

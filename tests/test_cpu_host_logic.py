@@ -377,3 +377,19 @@ def test_product_package_never_touches_the_oracle():
             _native.load()
     finally:
         _native._LIB_PATH, _native._lib = saved, saved_lib
+
+
+def test_driver_device_selection(monkeypatch):
+    """calibrate_and_model_tensor spreads independent integrations over devices (calibration.py:1160-1167) but never when
+    they are chained by init_guesses_from_previous_time_step (1210), never over more devices than units, and a pinned
+    device (the file driver's gpu_index, calibration.py:1741-1752) wins."""
+    from calamity_b200 import calibration as C
+
+    monkeypatch.delenv("CALAMITY_B200_DEVICE", raising=False)
+    monkeypatch.setenv("CALAMITY_B200_DEVICES", "0,2,5")
+    assert C._device_indices(60, False) == [0, 2, 5]
+    assert C._device_indices(2, False) == [0, 2]
+    assert C._device_indices(1, False) == [0]
+    assert C._device_indices(60, True) == [0]
+    monkeypatch.setenv("CALAMITY_B200_DEVICE", "3")
+    assert C._device_indices(60, False) == [3]
