@@ -495,7 +495,7 @@ def bench_integrations(args, rank, world, local_rank, dist):
     pr = float(np.sum(base.data_r.astype(np.float64) * base.wgts))
     pi = float(np.sum(base.data_i.astype(np.float64) * base.wgts))
     kw = dict(optimizer="Adamax", tol=0.0, learning_rate=1e-2, model_regularization=reg, prior_r_sum=pr, prior_i_sum=pi,
-              steps_per_sync=max(args.steps, args.warmup) + 1)
+              steps_per_sync=max(args.steps, args.warmup) + 1, use_graph=bool(args.graph))
 
     def run_unit(u, steps):
         plan.set_integration(u[0], u[1], u[2])
@@ -543,7 +543,7 @@ def bench_integrations(args, rank, world, local_rank, dist):
         d2h = (2 * units[0][3].nbytes + 4 * args.steps) * nint * world
         heavy_bytes = 4 * sizes["n_a_nz"] + 12 * sizes["n_d"] + 8 * sizes["n_c_nz"]
         hms = heavy_ms / (nint * args.steps)
-        achieved = heavy_bytes / (hms * 1e-3) / 1e9
+        achieved = heavy_bytes / (hms * 1e-3) / 1e9 if hms > 0 else 0.0
         line = {
             "metric": METRIC, "value": total_steps / (loop_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": loop_ms / (nint * args.steps), "higher_is_better": True, "scaling": "weak",
@@ -567,7 +567,7 @@ def bench_integrations(args, rank, world, local_rank, dist):
         }
         if info["n_class_slots"]:
             fpeak, fsrc = fma_peak_tflops(clocks)
-            tf = 2.0 * info["class_fma"] / (hms * 1e-3) / 1e12
+            tf = 2.0 * info["class_fma"] / (hms * 1e-3) / 1e12 if hms > 0 else 0.0
             line["roofline_fma"] = {"bound": "fp32_fma", "achieved": tf, "peak": fpeak, "unit": "TFLOP/s", "frac": tf / fpeak,
                                     "peak_source": fsrc}
         emit(line)

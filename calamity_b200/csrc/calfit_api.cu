@@ -1770,7 +1770,8 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
   int chunk = o->steps_per_sync > 0 ? o->steps_per_sync : 32;
   // use_graph: 1 = replay a captured graph, -1 = never, 0 = automatic: small problems are launch-latency bound (four
   // launches of a few microseconds each per iteration), so they replay a graph of `chunk` iterations
-  const bool small_problem = (size_t)pl->a_floats * sizeof(float) < ((size_t)256 << 20);
+  // (basis under 256 MB AND under 4 M visibilities: with the shared-basis layout the basis alone no longer says "small")
+  const bool small_problem = (size_t)pl->a_floats * sizeof(float) < ((size_t)256 << 20) && pl->nbls * (long long)pl->nfp < (4ll << 20);
   const bool want_graph = pl->nranks == 1 && (o->use_graph > 0 || (o->use_graph == 0 && small_problem && total >= 64));
   const bool time_heavy = !want_graph;
   std::vector<cudaEvent_t> evs;
