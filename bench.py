@@ -251,7 +251,13 @@ def bench_single_integration(args, rank, world, local_rank, dist):
 
     t_setup = time.perf_counter()
     prob = synth.make(args.workload)
-    full = prob.layout()
+    fdt = np.float64 if args.precision == 64 else np.float32
+    full = prob.layout(dtype=fdt)
+    if args.precision == 64:
+        if world > 1:
+            raise SystemExit("--precision 64 runs the generic path on one GPU")
+        for name in ("data_r", "data_i", "wgts", "g0_r", "g0_i", "c0_r", "c0_i"):
+            setattr(prob, name, getattr(prob, name).astype(np.float64))
     sizes = full.sizes()
     synth_s = time.perf_counter() - t_setup
     shard_mode = "class" if args.shared_basis >= 0 else "cyclic"
@@ -369,7 +375,8 @@ def bench_single_integration(args, rank, world, local_rank, dist):
         sh = shard.layout.sizes()
         # algorithmic bytes of ONE basis pass on this rank: non-padding basis rows once per group,
         # data_r / data_i / weights once, coefficients once; whole-iteration figure is B_iter
-        heavy_bytes = 4 * sh["n_a_nz"] + 12 * sh["n_d"] + 8 * sh["n_c_nz"]
+        esz = 8 if args.precision == 64 else 4
+        heavy_bytes = esz * sh["n_a_nz"] + 3 * esz * sh["n_d"] + 2 * esz * sh["n_c_nz"]
         shared_path = info["n_class_slots"] > 0
         traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu capture
@@ -382,12 +389,13 @@ def bench_single_integration(args, rank, world, local_rank, dist):
         heavy_avg_ms = heavy_ms / args.steps
         achieved = heavy_bytes / (heavy_avg_ms * 1e-3) / 1e9 if heavy_avg_ms > 0 else None
         iter_gbs = sizes["b_iter"] / (loop_ms / args.steps * 1e-3) / 1e9 / world
-        kernel = (f"shared_kernel<MS={32 if args.reg == 'sum' else 64},NQ={4 if args.reg == 'sum' else 2}>" if shared_path
-                  else f"heavy_kernel<FL={info['tile_freqs'] // 4},SUM={int(args.reg == 'sum')}>")
+        kernel = (f"shared_kernel<256|512,NQ={4 if args.reg == 'sum' else 2}> (two shapes, one basis pass)" if shared_path
+                  else ("generic forward + backward kernels (float64, two passes over the basis)" if info["generic"]
+                        else f"heavy_kernel<FL={info['tile_freqs'] // 4},SUM={int(args.reg == 'sum')}>"))
         line = {
             "metric": METRIC, "value": args.steps / (loop_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": loop_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
             "vs_baseline": (args.steps / (loop_ms * 1e-3) / PUBLISHED[args.workload])
             if args.workload in PUBLISHED and args.reg == "sum" else None,
             "config": workload_config(args, prob, sizes, world),
@@ -458,7 +466,7 @@ def bench_single_integration(args, rank, world, local_rank, dist):
             "loss_first_last": [float(h_s[0]), float(h_s[-1])] if len(h_s) else None,
             "what": "shared_basis=-1: every group streams its own basis copy from HBM once per iteration (the round-1 path)"}
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.precision == 32:
             threads = os.cpu_count() or 1
             r = cpu_port_rate(prob, args.reg, args.cpu_sample_bls, args.cpu_steps, 2, threads)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": r["sample"],
@@ -591,6 +599,8 @@ def main():
                     help="0: groups that share a basis block take the shared-basis kernel (default); -1: stream a private "
                          "copy per group (round-1 path)")
     ap.add_argument("--no-streaming", action="store_true", help="skip the re-measurement of the streaming path")
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64],
+                    help="64: the reference's --precision 64 / dtype=np.float64 (generic unfused device path, single GPU)")
     ap.add_argument("--integrations-per-gpu", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     # CPU arm: ~10-20 s of host work -- 2048 of the 61 075 baselines (dense padded basis 1.7 GB), 20 steps

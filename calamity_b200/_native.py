@@ -104,6 +104,7 @@ _SIGNATURES = {
     "calb2_last_error": (C.c_char_p, []),
     "calb2_version": (C.c_char_p, []),
     "calb2_device_count": (C.c_int, [C.POINTER(C.c_int32)]),
+    "calb2_debug_check_guards": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "calb2_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]),
     "calb2_plan_destroy": (C.c_int, [C.c_void_p]),
     "calb2_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),

@@ -310,6 +310,11 @@ def tensorize_gains(uvcal, polarization, time, dtype=np.float32):
     return _as_tensor(g.real, dtype=dtype), _as_tensor(g.imag, dtype=dtype)
 
 
+def _contraction_dtype(arrays):
+    """float64 when every tensor involved is float64 (the reference then contracts in float64), else float32."""
+    return np.dtype(np.float64) if all(np.asarray(a).dtype == np.float64 for a in arrays) else np.dtype(np.float32)
+
+
 def _nants_from(corr_inds, g_r=None):
     if g_r is not None:
         return int(np.shape(g_r)[0])
@@ -325,12 +330,16 @@ def yield_fg_model_array(
 ):
     """(nants, nants, nfreqs) float64 cube of sum_k coeff_k * comp_k, cell (i, j) only -- calibration.py:402-444.
     The contraction runs on the device."""
-    lay = RaggedLayout.from_dense([np.asarray(c) for c in fg_model_comps], corr_inds, nants)
-    flat = lay.flatten_coeffs([np.asarray(c) for c in fg_coeffs])
+    comps = [np.asarray(c) for c in fg_model_comps]
+    coeffs = [np.asarray(c) for c in fg_coeffs]
+    # float64 tensors are contracted in float64, as the reference does (the generic device path), everything else in float32
+    fdt = _contraction_dtype(comps + coeffs)
+    lay = RaggedLayout.from_dense(comps, corr_inds, nants, dtype=fdt)
+    flat = lay.flatten_coeffs(coeffs)
     with FitPlan(lay, device=_device_index()) as plan:
-        zeros = np.zeros((lay.nbls, lay.nfreqs), dtype=np.float32)
+        zeros = np.zeros((lay.nbls, lay.nfreqs), dtype=fdt)
         plan.set_integration(zeros, zeros, zeros)
-        plan.set_gains(np.ones((nants, nfreqs), dtype=np.float32), np.zeros((nants, nfreqs), dtype=np.float32))
+        plan.set_gains(np.ones((nants, nfreqs), dtype=fdt), np.zeros((nants, nfreqs), dtype=fdt))
         plan.set_coeffs(flat, np.zeros_like(flat))
         vis, _ = plan.get_model()
     cube = np.zeros((nants, nants, nfreqs))
@@ -822,11 +831,12 @@ def fg_model(fg_r, fg_i, fg_comps):
     comps = np.asarray(fg_comps)
     nvecs, ngrps, nbls, nfreqs = comps.shape
     corr = [[[(0, 0)] * nbls for _ in range(ngrps)]]
-    lay = RaggedLayout.from_dense([comps], corr, 1)
+    fdt = _contraction_dtype([comps, np.asarray(fg_r), np.asarray(fg_i)])
+    lay = RaggedLayout.from_dense([comps], corr, 1, dtype=fdt)
     with FitPlan(lay, device=_device_index()) as plan:
-        zeros = np.zeros((lay.nbls, nfreqs), dtype=np.float32)
+        zeros = np.zeros((lay.nbls, nfreqs), dtype=fdt)
         plan.set_integration(zeros, zeros, zeros)
-        plan.set_gains(np.ones((1, nfreqs), dtype=np.float32), np.zeros((1, nfreqs), dtype=np.float32))
+        plan.set_gains(np.ones((1, nfreqs), dtype=fdt), np.zeros((1, nfreqs), dtype=fdt))
         plan.set_coeffs(lay.flatten_coeffs([fg_r]), lay.flatten_coeffs([fg_i]))
         v_r, v_i = plan.get_model()
     return _as_tensor(v_r.reshape(ngrps, nbls, nfreqs)), _as_tensor(v_i.reshape(ngrps, nbls, nfreqs))

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -41,19 +42,56 @@ static int fail(int code, const char* fmt, ...) {
       return fail(CALB2_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
   } while (0)
 
+// Guard zones (CALB2_GUARD=1): compute-sanitizer is closed on the GPU pool this library is developed on, so
+// out-of-bounds WRITES are caught by the library itself -- every device allocation gets 256 pattern bytes on either
+// side, and calb2_debug_check_guards() (tests/test_gpu_guards.py) verifies that no kernel touched them.
+static constexpr size_t GUARD_BYTES = 256;
+static constexpr unsigned char GUARD_PATTERN = 0xA5;
+struct GuardRegistry {
+  std::mutex mu;
+  std::unordered_map<void*, size_t> live;  // base pointer -> payload bytes
+};
+static GuardRegistry& guards() {
+  static GuardRegistry g;
+  return g;
+}
+static bool guards_enabled() {
+  static const bool on = getenv("CALB2_GUARD") && atoi(getenv("CALB2_GUARD")) != 0;
+  return on;
+}
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  void* base = nullptr;  // != nullptr: allocation with guard zones, p = base + GUARD_BYTES
   cudaError_t alloc(size_t count) {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc(&p, count * sizeof(T));
+    if (!guards_enabled()) return cudaMalloc(&p, count * sizeof(T));
+    const size_t payload = (count * sizeof(T) + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&base, payload + 2 * GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(base, GUARD_PATTERN, payload + 2 * GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    p = reinterpret_cast<T*>(static_cast<unsigned char*>(base) + GUARD_BYTES);
+    std::lock_guard<std::mutex> lk(guards().mu);
+    guards().live[base] = payload;
+    return cudaSuccess;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (base) {
+      {
+        std::lock_guard<std::mutex> lk(guards().mu);
+        guards().live.erase(base);
+      }
+      cudaFree(base);
+    } else if (p) {
+      cudaFree(p);
+    }
     p = nullptr;
+    base = nullptr;
     n = 0;
   }
   size_t bytes() const { return n * sizeof(T); }
@@ -858,6 +896,34 @@ extern "C" {
 const char* calb2_last_error(void) { return g_err.c_str(); }
 const char* calb2_version(void) { return "calamity_b200 0.2 (sm_100a)"; }
 
+int calb2_debug_check_guards(int64_t* nbuffers, int64_t* nviolations) {
+  if (!nbuffers || !nviolations) return fail(CALB2_ERR_ARG, "null argument");
+  *nbuffers = 0;
+  *nviolations = 0;
+  if (!guards_enabled()) return fail(CALB2_ERR_STATE, "guard zones are off: set CALB2_GUARD=1 before the first allocation");
+  CU(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(guards().mu);
+  std::vector<unsigned char> h(GUARD_BYTES);
+  for (const auto& kv : guards().live) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, kv.first) != cudaSuccess) continue;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (attr.device != cur) continue;  // the caller checks one device at a time
+    ++*nbuffers;
+    for (int side = 0; side < 2; ++side) {
+      const unsigned char* src = static_cast<unsigned char*>(kv.first) + (side ? GUARD_BYTES + kv.second : 0);
+      CU(cudaMemcpy(h.data(), src, GUARD_BYTES, cudaMemcpyDeviceToHost));
+      for (unsigned char b : h)
+        if (b != GUARD_PATTERN) {
+          ++*nviolations;
+          break;
+        }
+    }
+  }
+  return 0;
+}
+
 int calb2_device_count(int32_t* count) {
   if (!count) return fail(CALB2_ERR_ARG, "null argument");
   int n = 0;
@@ -1322,7 +1388,7 @@ int calb2_plan_destroy(calb2_plan* pl) {
                          &pl->gm_r, &pl->gu_r, &pl->gm_i, &pl->gu_i, &pl->gsnap_r, &pl->gsnap_i, &pl->ggrad_r,
                          &pl->ggrad_i, &pl->c_r, &pl->c_i, &pl->cm_r, &pl->cu_r, &pl->cm_i, &pl->cu_i, &pl->csnap_r,
                          &pl->csnap_i, &pl->cgrad_r, &pl->cgrad_i, &pl->dcpart, &pl->hist, &pl->scratch_f, &pl->staging};
-  if (pl->nranks > 1) pl->ggrad_i.p = nullptr;  // a view into ggrad_r
+  if (pl->ggrad_i.n == 0) pl->ggrad_i.p = nullptr;  // (NCCL exchange) a view into ggrad_r
   for (auto* b : fb) b->release();
   pl->z.release();
   pl->y.release();

@@ -127,12 +127,12 @@ class SyntheticProblem:
         sub.wgts = np.ascontiguousarray(w / w.sum(), dtype=np.float32)
         return sub
 
-    def layout(self):
+    def layout(self, dtype=np.float32):
         from .layout import RaggedLayout
 
         ants_map = {a: a for a in range(self.nants)}
         chunked = {(1, int(self.ncomp.max())): self.comps_dict}
-        return RaggedLayout.from_chunked_dict(chunked, ants_map, self.nfreqs, nants=self.nants)
+        return RaggedLayout.from_chunked_dict(chunked, ants_map, self.nfreqs, nants=self.nants, dtype=dtype)
 
 
 # configs of BASELINE.json, in order

@@ -154,6 +154,10 @@ const char* calb2_version(void);
  * (calibration.py:1741-1752, 1796-1800); the drop-in driver spreads the independent (polarization, time) integrations of
  * calibration.py:1160-1167 over all of them, one plan per device. */
 int calb2_device_count(int32_t* count);
+/* Development aid (no counterpart in the reference): with CALB2_GUARD=1 in the environment every device allocation of the
+ * library carries 256 pattern bytes on either side; this call counts the live allocations on the current device and the
+ * guard zones a kernel has written into.  (compute-sanitizer is not available on the GPU pool this was developed on.) */
+int calb2_debug_check_guards(int64_t* nbuffers, int64_t* nviolations);
 
 /* Once per calibrate_and_model_tensor call: mirrors calibration.py:1143-1152. */
 int calb2_plan_create(const calb2_plan_desc* desc, calb2_plan** out);

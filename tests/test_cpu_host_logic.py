@@ -393,3 +393,34 @@ def test_driver_device_selection(monkeypatch):
     assert C._device_indices(60, True) == [0]
     monkeypatch.setenv("CALAMITY_B200_DEVICE", "3")
     assert C._device_indices(60, False) == [3]
+
+
+def test_get_auto_weights_inverse_variance_of_smoothed_autos():
+    """calibration.py:916-960: weights of baseline (i, j) = 1 / (smooth auto_i x smooth auto_j) on unflagged samples, 0 on
+    flagged ones, the autos smoothed by a least-squares fit of their real part to the DPSS modes of a `delay_extent` ns
+    window over the unflagged channels."""
+    from calamity_b200 import calibration as C
+    from calamity_b200 import modeling
+    from tests import fixtures_uv as fx
+
+    uvd = fx.line_array(ntimes=2, with_autos=True)
+    rng = np.random.default_rng(4)
+    freqs = uvd.freq_array[0]
+    comps = modeling.yield_dpss_model_comps_bl_grp(0.0, freqs, offset=25.0)
+    truth = {}
+    for a in range(6):  # smooth, positive autocorrelations inside the DPSS span + a little noise
+        coeff = np.zeros(comps.shape[1])
+        coeff[:3] = [40.0 + 5.0 * a, 3.0, -2.0]
+        truth[a] = comps @ coeff
+        rows = uvd.antpair2ind(a, a)
+        uvd.data_array[rows, 0, :, 0] = truth[a][None, :] + 1e-3 * rng.standard_normal((len(rows), len(freqs)))
+    uvd.flag_array[:] = rng.random(uvd.flag_array.shape) < 0.1
+    out = C.get_auto_weights(uvd, delay_extent=25.0)
+    assert out.weights_array.shape == uvd.data_array.shape
+    for (i, j) in [(0, 1), (2, 5), (3, 3)]:
+        rows = uvd.antpair2ind(i, j)
+        want = 1.0 / (truth[i] * truth[j])
+        got = out.weights_array[rows, 0, :, 0]
+        flg = uvd.flag_array[rows, 0, :, 0]
+        assert np.all(got[flg] == 0.0)
+        assert np.allclose(got[~flg], np.broadcast_to(want, got.shape)[~flg], rtol=2e-3)
