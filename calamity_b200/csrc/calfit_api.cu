@@ -75,6 +75,8 @@ struct DevBuf {
     if (e != cudaSuccess) return e;
     e = cudaMemset(base, GUARD_PATTERN, payload + 2 * GUARD_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaDeviceSynchronize();  // the fill runs on the legacy stream; the plan's streams are non-blocking and would race it
+    if (e != cudaSuccess) return e;
     p = reinterpret_cast<T*>(static_cast<unsigned char*>(base) + GUARD_BYTES);
     std::lock_guard<std::mutex> lk(guards().mu);
     guards().live[base] = payload;
@@ -238,7 +240,16 @@ template <class T>
 static int dalloc(DevBuf<T>& buf, size_t n, calb2_plan* pl, bool zero = true) {
   CU(buf.alloc(n));
   pl->device_bytes += buf.bytes();
-  if (zero && n) CU(cudaMemset(buf.p, 0, buf.bytes()));
+  // stream-ordered: the plan's streams are non-blocking, a fill on the legacy stream would not be ordered with the kernels
+  // that use the buffer next (found by the guard-zone run: a late fill overwrote freshly uploaded job descriptors)
+  if (zero && n) {
+    if (pl->stream)
+      CU(cudaMemsetAsync(buf.p, 0, buf.bytes(), pl->stream));
+    else {
+      CU(cudaMemset(buf.p, 0, buf.bytes()));
+      CU(cudaDeviceSynchronize());
+    }
+  }
   return 0;
 }
 
@@ -2012,7 +2023,7 @@ int calb2_comm_init(calb2_plan* pl, const void* id, int32_t rank, int32_t nranks
   pl->ggrad_i.release();
   const size_t ng = (size_t)pl->nants * pl->nfp;
   CU(pl->ggrad_r.alloc(2 * ng));
-  CU(cudaMemset(pl->ggrad_r.p, 0, 2 * ng * sizeof(float)));
+  CU(cudaMemsetAsync(pl->ggrad_r.p, 0, 2 * ng * sizeof(float), pl->stream));
   pl->ggrad_i.p = pl->ggrad_r.p + ng;  // view; never released separately
   pl->ggrad_i.n = 0;
   return 0;
@@ -2066,7 +2077,8 @@ int calb2_comm_peer_import(calb2_plan* pl, const void* ipc_handles, int32_t rank
   if (const char* t = getenv("CALB2_PEER_TIMEOUT_MS")) pl->xtimeout_ns = (unsigned long long)std::max(1.0, atof(t)) * 1000000ull;
   if (!pl->tail_counter.p) {
     CU(pl->tail_counter.alloc(1));
-    CU(cudaMemset(pl->tail_counter.p, 0, sizeof(unsigned int)));
+    CU(cudaMemsetAsync(pl->tail_counter.p, 0, sizeof(unsigned int), pl->stream));
+    CU(cudaStreamSynchronize(pl->stream));
   }
   return 0;
 }

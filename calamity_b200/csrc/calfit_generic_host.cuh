@@ -42,7 +42,7 @@ struct GenericPlan : GenericBase {
   int alloc(DevBuf<U>& b, size_t n, bool zero = true) {
     CU(b.alloc(n));
     bytes += b.bytes();
-    if (zero && n) CU(cudaMemset(b.p, 0, b.bytes()));
+    if (zero && n) CU(cudaMemsetAsync(b.p, 0, b.bytes(), pl->stream));  // stream-ordered (the plan's streams are non-blocking)
     return 0;
   }
 
