@@ -94,6 +94,8 @@ class PlanInfo(C.Structure):
         ("n_a_class", C.c_int64),
         ("n_a_class_nz", C.c_int64),
         ("class_fma", C.c_int64),
+        ("n_tc_ctas", C.c_int64),
+        ("n_tc_slots", C.c_int64),
     ]
 
 
@@ -105,6 +107,7 @@ _SIGNATURES = {
     "calb2_version": (C.c_char_p, []),
     "calb2_device_count": (C.c_int, [C.POINTER(C.c_int32)]),
     "calb2_debug_check_guards": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "calb2_debug_tc_record": (C.c_int, [C.POINTER(C.c_uint32)]),
     "calb2_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]),
     "calb2_plan_destroy": (C.c_int, [C.c_void_p]),
     "calb2_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),

@@ -18,6 +18,7 @@
 #include "../../include/calamity_b200.h"
 #include "calfit_kernels.cuh"
 #include "calfit_shared.cuh"
+#include "calfit_tc.cuh"
 #include "calfit_setup.cuh"
 #include "calfit_generic.cuh"
 
@@ -35,11 +36,14 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static volatile unsigned int* g_tc_dbg = nullptr;  // last plan's tensor-core wait record (development aid)
 #define CU(call)                                                                                         \
   do {                                                                                                   \
     cudaError_t e__ = (call);                                                                            \
     if (e__ != cudaSuccess)                                                                              \
-      return fail(CALB2_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return fail(CALB2_ERR_CUDA, "%s failed at %s:%d: %s [tc wait record: code %u tile %u cta %u thread %u]", #call, __FILE__, __LINE__, \
+                  cudaGetErrorString(e__), g_tc_dbg ? g_tc_dbg[0] : 0u, g_tc_dbg ? g_tc_dbg[1] : 0u, g_tc_dbg ? g_tc_dbg[2] : 0u,   \
+                  g_tc_dbg ? g_tc_dbg[3] : 0u);                                                            \
   } while (0)
 
 // Guard zones (CALB2_GUARD=1): compute-sanitizer is closed on the GPU pool this library is developed on, so
@@ -169,6 +173,11 @@ struct calb2_plan {
     int kp, ncomp;
     int nmembers;
     bool uploaded;
+    // tensor-core shape (calfit_tc.cuh): classes of <= 128 vectors keep four more copies of every tile (MN-major / K-major,
+    // hi / lo) in At
+    bool tc;
+    int kpt;          // ncomp rounded up to 16
+    long long tc_off; // float offset of the class's [tile][4][kpt][32] block in At
   };
   std::vector<ClsInfo> classes;
   std::vector<int> grp_cls;           // dense class index of the group, or -1: streaming path
@@ -176,6 +185,13 @@ struct calb2_plan {
   // shape 0: 256 threads, classes of <= 160 vectors, two CTAs per SM; shape 1: 512 threads, <= 208 vectors
   std::vector<MTileDesc> mtiles[2][2];
   DevBuf<MTileDesc> d_mtiles[2][2];
+  // tensor-core shape: its CTAs (64 groups of a class of <= 128 vectors) and, when it is in use, the 256-thread CTAs of the
+  // remaining small classes (129-160 vectors)
+  std::vector<MTileDesc> mt_tc, mt_small_rest;
+  DevBuf<MTileDesc> d_mt_tc, d_mt_small_rest;
+  DevBuf<float> At;
+  bool tc_enabled = false;
+  unsigned int* tc_dbg = nullptr;     // mapped host memory: record of a tensor-core wait that timed out
   int nseg[2] = {1, 1};               // channel segments per class tile = planes of dcpart in use
   long long dc_plane = 0;             // floats per plane of dcpart
   int first_class_row = 0;            // rows below it belong to the streaming path (plane 0 only)
@@ -369,7 +385,12 @@ static int shared_ms(int v, int shape) { return (shape == 0 ? 64 : 128) / (v == 
 // all of them write z / dcpart / partials for their own baselines and rows.
 static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
   const int v = sum ? 1 : 0;
-  const int n_small = (int)pl->mtiles[v][0].size(), n_large = (int)pl->mtiles[v][1].size();
+  // tensor-core shape: the fit's own passes (plain chi^2); initialisation / model-only passes and 'sum' stay on the CUDA cores
+  const bool use_tc = pl->tc_enabled && !sum && !hp.init_mode && !hp.store_v && !pl->mt_tc.empty();
+  const int n_tc = use_tc ? (int)pl->mt_tc.size() : 0;
+  const MTileDesc* small_tiles = use_tc ? pl->d_mt_small_rest.p : pl->d_mtiles[v][0].p;
+  const int n_small = use_tc ? (int)pl->mt_small_rest.size() : (int)pl->mtiles[v][0].size();
+  const int n_large = (int)pl->mtiles[v][1].size();
   SharedParams sp{};
   if (n_small + n_large > 0) {
     sp.A = hp.A;
@@ -422,8 +443,42 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
     }
     if (e != cudaSuccess) return e;
   }
+  if (n_tc > 0) {
+    TcParams tp{};
+    tp.At = pl->At.p;
+    tp.tiles = pl->d_mt_tc.p;
+    tp.cslots = pl->d_cslots.p;
+    tp.bl_ant0 = hp.bl_ant0;
+    tp.bl_ant1 = hp.bl_ant1;
+    tp.d_r = hp.d_r;
+    tp.d_i = hp.d_i;
+    tp.w = hp.w;
+    for (int b = 0; b < 2; ++b) {
+      tp.g_r[b] = hp.g_r[b];
+      tp.g_i[b] = hp.g_i[b];
+    }
+    tp.c_r = hp.c_r;
+    tp.c_i = hp.c_i;
+    tp.z = hp.z;
+    tp.dcpart = hp.dcpart;
+    tp.dc_plane = pl->dc_plane;
+    tp.partials = hp.partials + (size_t)(nitems + n_small + n_large) * 4;
+    tp.st = hp.st;
+    tp.nfp = hp.nfp;
+    tp.dbg = pl->tc_dbg;
+    static bool configured[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(shared_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg::SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+      configured[dev] = true;
+    }
+    shared_tc_kernel<<<n_tc, TcCfg::NTHR, TcCfg::SMEM_BYTES, s>>>(tp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   if (n_small > 0) {
-    sp.tiles = pl->d_mtiles[v][0].p;
+    sp.tiles = small_tiles;
     sp.partials = hp.partials + (size_t)nitems * 4;
     cudaError_t e = launch_shared_shape(sum, pl->cls_single_bl, 0, sp, n_small, s);
     if (e != cudaSuccess) return e;
@@ -431,9 +486,17 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
   if (fork_large) return cudaStreamWaitEvent(s, pl->ev_join, 0);
   return cudaSuccess;
 }
+// partial-sum slots of one pass; with the tensor-core shape in use the layout is items | small rest | large | tensor-core
 static int n_partials(const calb2_plan* pl, bool sum) {
   const int v = sum ? 1 : 0;
+  if (pl->tc_enabled && !sum && !pl->mt_tc.empty())
+    return (int)(pl->items.size() + pl->mt_small_rest.size() + pl->mtiles[0][1].size() + pl->mt_tc.size());
   return (int)(pl->items.size() + pl->mtiles[v][0].size() + pl->mtiles[v][1].size());
+}
+static int n_partials_max(const calb2_plan* pl) {
+  int n = 0;
+  for (int v = 0; v < 2; ++v) n = std::max(n, (int)(pl->items.size() + pl->mtiles[v][0].size() + pl->mtiles[v][1].size()));
+  return std::max(n, (int)(pl->items.size() + pl->mt_small_rest.size() + pl->mtiles[0][1].size() + pl->mt_tc.size()));
 }
 
 static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, int store_v, int init_mode) {
@@ -935,6 +998,12 @@ int calb2_debug_check_guards(int64_t* nbuffers, int64_t* nviolations) {
   return 0;
 }
 
+int calb2_debug_tc_record(uint32_t* out16) {
+  if (!out16) return fail(CALB2_ERR_ARG, "null argument");
+  for (int i = 0; i < 16; ++i) out16[i] = g_tc_dbg ? g_tc_dbg[i] : 0u;
+  return 0;
+}
+
 int calb2_device_count(int32_t* count) {
   if (!count) return fail(CALB2_ERR_ARG, "null argument");
   int n = 0;
@@ -1168,6 +1237,9 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
       ci.a_off = off;
       ci.uploaded = false;
       off += (long long)ci.kp * pl->nfp;
+      ci.kpt = ((ci.ncomp + 15) / 16) * 16;
+      ci.tc = ci.kpt <= TcCfg::KPMAX;
+      ci.tc_off = 0;
       const int first_cs = (int)cslots.size();
       for (int g : mem) {
         const int is = pl->grp_slot0[g];
@@ -1186,6 +1258,18 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
       (void)first_cs;
     }
     pl->a_class_floats = off - heavy_floats;
+  }
+  {
+    // tensor-core shape: on by default for single-baseline slots; CALB2_TC=0 keeps every class on the CUDA-core shapes
+    pl->tc_enabled = pl->cls_single_bl && !(getenv("CALB2_TC") && atoi(getenv("CALB2_TC")) == 0);
+    long long tc_off = 0;
+    for (auto& ci : pl->classes) {
+      if (!pl->tc_enabled) ci.tc = false;
+      if (ci.tc) {
+        ci.tc_off = tc_off;
+        tc_off += (long long)pl->ntiles_c * 4 * ci.kpt * SHARED_FT;
+      }
+    }
   }
   {
     // CTAs: a class is cut into tiles of MS groups; when that gives too few CTAs to balance 148 SMs (two resident CTAs
@@ -1216,15 +1300,34 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
             mt.j1 = (int)((long long)pl->ntiles_c * (sg + 1) / nseg);
             mt.seg = sg;
             pl->mtiles[v][shape].push_back(mt);
+            if (v == 0 && shape == 0 && !ci.tc) pl->mt_small_rest.push_back(mt);
           }
+        if (v == 0 && ci.tc)  // the same class as 64-group tiles of the tensor-core shape
+          for (int m0 = 0; m0 < ci.nmembers; m0 += TcCfg::MS)
+            for (int sg = 0; sg < nseg; ++sg) {
+              MTileDesc mt{};
+              mt.a_off = ci.tc_off;
+              mt.kp = ci.kpt;
+              mt.ncomp = ci.ncomp;
+              mt.nslots = std::min(TcCfg::MS, ci.nmembers - m0);
+              mt.cs0 = cs_cursor + m0;
+              mt.j0 = (int)((long long)pl->ntiles_c * sg / nseg);
+              mt.j1 = (int)((long long)pl->ntiles_c * (sg + 1) / nseg);
+              mt.seg = sg;
+              pl->mt_tc.push_back(mt);
+            }
         cs_cursor += ci.nmembers;
       }
-      for (int shape = 0; shape < 2; ++shape)  // longest first: cost ~ channel tiles x rows x (8-group blocks in use)
-        std::stable_sort(pl->mtiles[v][shape].begin(), pl->mtiles[v][shape].end(), [](const MTileDesc& a, const MTileDesc& b) {
-          const long long ca = (long long)(a.j1 - a.j0) * (a.kp + 40) * ((a.nslots + 7) / 8);
-          const long long cb = (long long)(b.j1 - b.j0) * (b.kp + 40) * ((b.nslots + 7) / 8);
-          return ca > cb;
-        });
+      auto by_cost = [](const MTileDesc& a, const MTileDesc& b) {  // longest first: channel tiles x rows x (8-group blocks in use)
+        const long long ca = (long long)(a.j1 - a.j0) * (a.kp + 40) * ((a.nslots + 7) / 8);
+        const long long cb = (long long)(b.j1 - b.j0) * (b.kp + 40) * ((b.nslots + 7) / 8);
+        return ca > cb;
+      };
+      for (int shape = 0; shape < 2; ++shape) std::stable_sort(pl->mtiles[v][shape].begin(), pl->mtiles[v][shape].end(), by_cost);
+      if (v == 0) {
+        std::stable_sort(pl->mt_small_rest.begin(), pl->mt_small_rest.end(), by_cost);
+        std::stable_sort(pl->mt_tc.begin(), pl->mt_tc.end(), by_cost);
+      }
     }
   }
   pl->slot_row0[ns] = (int)rows;
@@ -1364,7 +1467,15 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(dalloc(pl->cu_i, (size_t)nc, pl));
   pl->dc_plane = rows * 4;
   TRY(dalloc(pl->dcpart, (size_t)pl->dc_plane * std::max(pl->nseg[0], pl->nseg[1]), pl));
-  TRY(dalloc(pl->partials, (size_t)std::max(n_partials(pl, false), n_partials(pl, true)) * 4, pl));
+  TRY(dalloc(pl->partials, (size_t)n_partials_max(pl) * 4, pl));
+  TRY(upload(pl->d_mt_tc, pl->mt_tc, pl));
+  TRY(upload(pl->d_mt_small_rest, pl->mt_small_rest, pl));
+  {
+    long long tc_floats = 0;
+    for (const auto& ci : pl->classes)
+      if (ci.tc) tc_floats = std::max(tc_floats, ci.tc_off + (long long)pl->ntiles_c * 4 * ci.kpt * SHARED_FT);
+    TRY(dalloc(pl->At, (size_t)tc_floats, pl));
+  }
   TRY(dalloc(pl->red_d, 4096, pl));
   TRY(dalloc(pl->dbg_out, 16, pl));
   TRY(dalloc(pl->state, 1, pl));
@@ -1378,6 +1489,14 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     rc = fail(CALB2_ERR_CUDA, "cudaMallocHost(staging) failed");
   if (!rc && cudaMallocHost(&pl->h_state, sizeof(FitState)) != cudaSuccess)
     rc = fail(CALB2_ERR_CUDA, "cudaMallocHost(state) failed");
+  if (!rc && pl->tc_enabled) {
+    if (cudaHostAlloc(&pl->tc_dbg, 64, cudaHostAllocMapped) != cudaSuccess)
+      rc = fail(CALB2_ERR_CUDA, "cudaHostAlloc(tc_dbg) failed");
+    else {
+      memset(pl->tc_dbg, 0, 64);
+      g_tc_dbg = pl->tc_dbg;
+    }
+  }
   if (rc) {
     calb2_plan_destroy(pl);
     return rc;
@@ -1412,6 +1531,9 @@ int calb2_plan_destroy(calb2_plan* pl) {
   pl->d_items.release();
   for (int v = 0; v < 2; ++v)
     for (int shape = 0; shape < 2; ++shape) pl->d_mtiles[v][shape].release();
+  pl->d_mt_tc.release();
+  pl->d_mt_small_rest.release();
+  pl->At.release();
   pl->d_cslots.release();
   pl->d_cs_slot.release();
   pl->d_slot_nb.release();
@@ -1427,6 +1549,10 @@ int calb2_plan_destroy(calb2_plan* pl) {
   pl->sky_i.release();
   if (pl->h_staging) cudaFreeHost(pl->h_staging);
   if (pl->h_state) cudaFreeHost(pl->h_state);
+  if (pl->tc_dbg) {
+    if (g_tc_dbg == pl->tc_dbg) g_tc_dbg = nullptr;
+    cudaFreeHost(pl->tc_dbg);
+  }
   pl->tail_counter.release();
   if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->ev_join) cudaEventDestroy(pl->ev_join);
@@ -1453,6 +1579,11 @@ int calb2_plan_get_info(const calb2_plan* pl, calb2_plan_info* info) {
   info->n_classes = (int64_t)pl->classes.size();
   info->n_class_slots = pl->nslots_class;
   info->n_class_ctas = (int64_t)(pl->mtiles[0][0].size() + pl->mtiles[0][1].size());
+  info->n_tc_ctas = pl->tc_enabled ? (int64_t)pl->mt_tc.size() : 0;
+  info->n_tc_slots = 0;
+  if (pl->tc_enabled)
+    for (const auto& ci : pl->classes)
+      if (ci.tc) info->n_tc_slots += ci.nmembers;
   info->n_a_class = pl->a_class_floats;
   info->n_a_class_nz = 0;
   info->class_fma = 0;
@@ -1477,9 +1608,11 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* con
   if (pl->gen) return pl->gen->set_basis(g0, ng, blocks_v);
   const float* const* blocks = reinterpret_cast<const float* const*>(blocks_v);
   std::vector<RetileJob> jobs;
+  std::vector<TcRetileJob> tc_jobs;
   std::unordered_map<const float*, long long> seen;
   size_t used = 0;
   DevBuf<RetileJob> djobs;
+  DevBuf<TcRetileJob> d_tc_jobs;
   auto flush = [&]() -> int {
     if (jobs.empty()) return 0;
     CU(cudaMemcpyAsync(pl->staging.p, pl->h_staging, used * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
@@ -1487,8 +1620,15 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* con
     CU(cudaMemcpyAsync(djobs.p, jobs.data(), jobs.size() * sizeof(RetileJob), cudaMemcpyHostToDevice, pl->stream));
     retile_kernel<<<(unsigned)jobs.size(), 256, 0, pl->stream>>>(pl->staging.p, pl->A.p, djobs.p, pl->nf, pl->FT);
     CU(cudaGetLastError());
+    if (!tc_jobs.empty()) {
+      if (d_tc_jobs.n < tc_jobs.size()) CU(d_tc_jobs.alloc(tc_jobs.size() * 2));
+      CU(cudaMemcpyAsync(d_tc_jobs.p, tc_jobs.data(), tc_jobs.size() * sizeof(TcRetileJob), cudaMemcpyHostToDevice, pl->stream));
+      retile_tc_kernel<<<(unsigned)tc_jobs.size(), 256, 0, pl->stream>>>(pl->staging.p, pl->At.p, d_tc_jobs.p, pl->nf);
+      CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(pl->stream));
     jobs.clear();
+    tc_jobs.clear();
     seen.clear();
     used = 0;
     return 0;
@@ -1524,6 +1664,14 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* con
       jb.row_in_item = 0;
       jb.swz_ft = SHARED_FT;
       jobs.push_back(jb);
+      if (pl->classes[cls].tc) {
+        TcRetileJob tj{};
+        tj.src_off = base;
+        tj.dst_off = pl->classes[cls].tc_off;
+        tj.ncomp = ncomp;
+        tj.kpt = pl->classes[cls].kpt;
+        tc_jobs.push_back(tj);
+      }
       pl->classes[cls].uploaded = true;
       continue;
     }
@@ -1542,6 +1690,7 @@ int calb2_plan_set_basis(calb2_plan* pl, int32_t g0, int32_t ng, const void* con
   }
   if (int r = flush()) return r;
   djobs.release();
+  d_tc_jobs.release();
   pl->basis_groups_set += ng;
   return 0;
 }

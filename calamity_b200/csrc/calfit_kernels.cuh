@@ -1367,6 +1367,33 @@ __global__ void retile_kernel(const float* __restrict__ staging, float* __restri
   }
 }
 
+// staging [ncomp][nfreqs] -> the four tensor-core copies of a class (calfit_tc.cuh): per 32-channel tile
+// [b32 hi | b32 lo | std hi | std lo], each [kpt][32]: hi = the value truncated to tf32, lo = the rest; "b32" rows carry the
+// 32-byte-base swizzle of the MN-major operand (32-byte pieces ^ (row & 3)), "std" rows the 16-byte one of the K-major operand
+struct TcRetileJob {
+  long long src_off;
+  long long dst_off;
+  int ncomp;
+  int kpt;
+};
+__global__ void retile_tc_kernel(const float* __restrict__ staging, float* __restrict__ At, const TcRetileJob* jobs, int nfreqs) {
+  const TcRetileJob jb = jobs[blockIdx.x];
+  const long long n = (long long)jb.ncomp * nfreqs;
+  for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+    const int k = (int)(e / nfreqs), f = (int)(e % nfreqs);
+    const int tile = f >> 5, fi = f & 31;
+    const float x = staging[jb.src_off + e];
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
+    float* t = At + jb.dst_off + (long long)tile * 4 * jb.kpt * 32 + (long long)k * 32;
+    const int p32 = (((fi >> 3) ^ (k & 3)) << 3) | (fi & 7);
+    const int p16 = (((fi >> 2) ^ (k & 7)) << 2) | (fi & 3);
+    t[p32] = hi;
+    t[(long long)jb.kpt * 32 + p32] = lo;
+    t[(long long)2 * jb.kpt * 32 + p16] = hi;
+    t[(long long)3 * jb.kpt * 32 + p16] = lo;
+  }
+}
+
 // [n][nfreqs] host layout <-> [n][nfp] padded device layout
 __global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int nfreqs, int nfp,
                                 float fill) {

@@ -1,0 +1,465 @@
+// Tensor-core shape of the shared-basis pass (sm_100a: tcgen05 + TMEM), for basis classes of <= 128 vectors, plain chi^2,
+// single-baseline slots.  Same work item as calfit_shared.cuh -- 64 groups of ONE class through a range of 32-channel tiles --
+// with both contractions on the 5th-generation tensor cores as TF32 MMAs with a 3-term split (hi.hi + hi.lo + lo.hi; plain TF32
+// would break the 1e-5 loss tolerance):
+//
+//   phase F   V[128 x 32]  = C[128 x kp] . A[kp x 32]        A-operand = coefficients, hi part resident in TMEM (written once per
+//                                                             CTA), lo part a K-major SWIZZLE_128B operand in shared memory;
+//                                                             B-operand = the tile, MN-major (SWIZZLE_128B_BASE32B: the only
+//                                                             MN-major layout tf32 has), hi and lo copies
+//   phase Q   the streaming kernel's arithmetic (calibration.py:1593-1609) by 8 warps on the CUDA cores: a thread owns TMEM lane
+//             m = 2 group + part, reads its row of V (tcgen05.ld), pairs re/im with its neighbour lane by shuffles, and writes
+//             dL/dv back to TMEM as the next A-operand (hi over V, lo next to it)
+//   phase B   dC[128 x kp] += Q[128 x 32] . A[kp x 32]^T      A-operand = dL/dv hi / lo in TMEM, B-operand = the tile, K-major
+//                                                             SWIZZLE_128B, hi and lo copies; the accumulator stays in TMEM for
+//                                                             all tiles of the CTA
+//
+// The tensor core accumulates in float32 with truncation (measured: tools/tc_probe.cu, profiles/round2_tcgen05_probe.log: 26
+// chained accumulations cost 6e-7 relative).  V therefore goes to FOUR partial accumulators (a quarter of the k-steps each)
+// plus one for the two small split terms, and the five are added in registers with round-to-nearest.
+//
+// One warp issues the MMAs and the bulk copies (one thread), eight warps do phase Q; mbarriers connect them:
+//   full[s]  tile landed (TMA)            -> MMA warp          free[s]  phase B of the tile in stage s retired (tcgen05.commit) -> MMA warp refills s
+//   bar_v    phase F retired (commit)     -> phase-Q warps     bar_q    phase Q done (256 arrivals)                             -> MMA warp issues B
+// Descriptor encodings follow cute/arch/mma_sm100_desc.hpp; every operand form used here is checked by tools/tc_probe.cu.
+#pragma once
+#include "calfit_shared.cuh"
+
+namespace calb2 {
+
+struct TcCfg {
+  static constexpr int MS = 64, FT = 32;
+  static constexpr int KPMAX = 128;                          // rows per class tile (ncomp rounded up to 16)
+  static constexpr int NEPI = 256;                           // 8 phase-Q warps: TMEM lane quadrant = warp & 3, column half = warp >> 2
+  static constexpr int NTHR = NEPI + 32;                     // + the MMA / TMA warp
+  static constexpr int STAGE_BYTES = 4 * KPMAX * 128;        // [b32 hi | b32 lo | std hi | std lo], 64 KB
+  static constexpr int OFF_STAGE = 0;
+  static constexpr int OFF_CLO = 2 * STAGE_BYTES;            // C lo: [kp / 32 chunks][128 rows][128 B], K-major SWIZZLE_128B
+  static constexpr int OFF_CS = OFF_CLO + (KPMAX / 32) * 128 * 128;
+  static constexpr int OFF_ANT = OFF_CS + MS * 16;
+  static constexpr int OFF_RED = OFF_ANT + MS * 8;
+  static constexpr int OFF_BAR = OFF_RED + 8 * 16;           // full[2], free[2], v, q
+  static constexpr int OFF_TMEM = OFF_BAR + 6 * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEM + 16;
+  // TMEM columns (512 allocated)
+  static constexpr int COL_CHI = 0;     // C hi, 128
+  static constexpr int COL_DC = 128;    // dC accumulator, 128
+  static constexpr int COL_V = 256;     // 4 partial V accumulators of 32; dL/dv hi is written over the first
+  static constexpr int COL_VC = 384;    // accumulator of the two small split terms
+  static constexpr int COL_QLO = 416;   // dL/dv lo
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version 1 (Blackwell)
+  d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+// K-major SWIZZLE_128B operand: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) { return umma_desc(smem_addr, 16, 1024, 2); }
+// MN-major tf32 operand, 32 columns, 8 k-rows = two 4-row atoms of the 32-byte-base swizzle, 512 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t smem_addr) { return umma_desc(smem_addr, 512, 512, 1); }
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
+  uint32_t r[16];
+  // load + wait in ONE asm statement: the registers are only defined after tcgen05.wait::ld, and nothing may be scheduled between
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(addr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+               "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+               "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+               "r"(__float_as_uint(v[15]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void mbar_arrive_plain(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Bounded wait: a protocol error must not hang the GPU.  mbarrier.try_wait suspends the thread in hardware (cheap, no polling
+// traffic); every 16th return without completion the waiter looks at the clock, and after 4 s records (code, tile, CTA, thread)
+// in a mapped host buffer and traps; calb2 reports the record with the CUDA error.
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned int code, int j) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  unsigned int polls = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((++polls & 15u) == 0u) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {
+        if (dbg) {
+          dbg[1] = (unsigned int)j;
+          dbg[2] = blockIdx.x;
+          dbg[3] = threadIdx.x;
+          __threadfence_system();
+          dbg[0] = code;
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tc_mark(unsigned int* dbg, int slot, unsigned int value) {
+  if (dbg && blockIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned int*>(dbg + slot) = value;
+    __threadfence_system();
+  }
+}
+
+struct TcParams {
+  const float* At;      // tensor-core copies of the class tiles: per class [tile][4][kpt][32]
+  const MTileDesc* tiles;  // a_off = float offset of the class in At, kp = kpt (multiple of 16)
+  const ClassSlot* cslots;
+  const int* bl_ant0;
+  const int* bl_ant1;
+  const float* d_r;
+  const float* d_i;
+  const float* w;
+  const float* g_r[2];
+  const float* g_i[2];
+  const float* c_r;
+  const float* c_i;
+  float2* z;
+  float* dcpart;
+  long long dc_plane;
+  double* partials;
+  const FitState* st;
+  int nfp;
+  unsigned int* dbg;    // mapped host memory: [0] = code of a wait that timed out, [1] tile, [2] CTA, [3] thread
+};
+
+__global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParams p) {
+  using C = TcCfg;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const FitState* st = p.st;
+  if (st->step > st->stop_after) return;  // fit already stopped (uniform across the grid)
+  const MTileDesc mt = p.tiles[blockIdx.x];
+  const int gsel = st->step & 1;
+  const float* __restrict__ g_r = p.g_r[gsel];
+  const float* __restrict__ g_i = p.g_i[gsel];
+
+  unsigned char* stage0 = smem + C::OFF_STAGE;
+  float* Clo = reinterpret_cast<float*>(smem + C::OFF_CLO);
+  ClassSlot* s_cs = reinterpret_cast<ClassSlot*>(smem + C::OFF_CS);
+  int2* s_ant = reinterpret_cast<int2*>(smem + C::OFF_ANT);
+  float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t *bar_full = bars, *bar_free = bars + 2, *bar_v = bars + 4, *bar_q = bars + 5;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kpt = mt.kp, nslots = mt.nslots;
+  const int ntiles = mt.j1 - mt.j0;
+  const uint32_t sub_bytes = (uint32_t)kpt * 128u;       // one of the four copies of a tile
+  const uint32_t stage_bytes = 4u * sub_bytes;
+  const float* Abase = p.At + mt.a_off + (size_t)mt.j0 * kpt * 4 * 32;
+  const bool mma_warp = warp == 8;
+
+  if (mma_warp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (lane == 0) {
+      mbar_init(&bar_full[0], 1);
+      mbar_init(&bar_full[1], 1);
+      mbar_init(&bar_free[0], 1);
+      mbar_init(&bar_free[1], 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_q, C::NEPI);
+      mbar_fence_init();
+      mbar_expect_tx(&bar_full[0], stage_bytes);
+      bulk_g2s(stage0, Abase, stage_bytes, &bar_full[0]);
+      if (ntiles > 1) {
+        mbar_expect_tx(&bar_full[1], stage_bytes);
+        bulk_g2s(stage0 + C::STAGE_BYTES, Abase + (size_t)kpt * 4 * 32, stage_bytes, &bar_full[1]);
+      }
+    }
+  }
+  if (tid < C::MS) {
+    ClassSlot cs = {0, 0, 0, 0};
+    int2 ants = make_int2(0, 0);
+    if (tid < nslots) {
+      cs = p.cslots[mt.cs0 + tid];
+      ants = make_int2(p.bl_ant0[cs.bl0] * p.nfp, p.bl_ant1[cs.bl0] * p.nfp);
+    }
+    s_cs[tid] = cs;
+    s_ant[tid] = ants;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  // ---- phase-Q thread identity: TMEM lane m = 2 group + part; the warp's quadrant of lanes; its half of the 32 columns
+  const int quad = warp & 3, half = (warp >> 2) & 1;
+  const int m = quad * 32 + lane, s = m >> 1, part = m & 1;
+  const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+  const bool valid = !mma_warp && s < nslots;
+
+  // ---- coefficients: hi part -> TMEM (the A-operand of phase F for the whole pass), lo part -> shared memory operand
+  if (!mma_warp) {
+    const float* src = (part ? p.c_i : p.c_r) + s_cs[s].coef0;
+    const int k_lo = half * (kpt / 2), k_hi = k_lo + kpt / 2;  // kpt / 2 is a multiple of 8
+    for (int k0 = k_lo; k0 < k_hi; k0 += 8) {
+      float hi[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + i;
+        const float c = (valid && k < mt.ncomp) ? src[k] : 0.f;
+        hi[i] = tf32_trunc(c);
+        // K-major SWIZZLE_128B: chunk of 32 k, row m, 16-byte pieces XOR-ed with (m & 7)
+        Clo[(k >> 5) * 128 * 32 + m * 32 + (((((k & 31) >> 2) ^ (m & 7)) << 2) | (k & 3))] = c - hi[i];
+      }
+      tmem_st8(tmem + tlane + C::COL_CHI + k0, hi);
+    }
+    tmem_st_wait();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // C lo was written by ordinary stores, the MMA reads it through the async proxy
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (mma_warp) {
+    // =====================================================================================================================
+    // MMA / TMA warp: one thread issues everything
+    // =====================================================================================================================
+    if (lane == 0) {
+      const uint32_t idesc_f = umma_idesc_tf32(128, 32, 1);
+      const uint32_t idesc_b = umma_idesc_tf32(128, kpt, 0);
+      const uint32_t clo_addr = smem_u32(Clo);
+      const int nks = kpt / 8;
+      const int per = (nks + 3) / 4;  // k-steps per partial V accumulator
+      uint32_t dc_accum = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        const int sg = j & 1;
+        const uint32_t sbase = smem_u32(stage0 + sg * C::STAGE_BYTES);
+        tc_wait(&bar_full[sg], (j >> 1) & 1, p.dbg, 1, j);
+        tc_fence_after();
+        // ---- phase F: V_p += C_hi . A_hi ; V_c += C_hi . A_lo + C_lo . A_hi
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint64_t b_hi = umma_desc_mn32(sbase + (uint32_t)ks * 1024u);
+          const uint64_t b_lo = umma_desc_mn32(sbase + sub_bytes + (uint32_t)ks * 1024u);
+          const uint32_t a_hi = tmem + C::COL_CHI + 8 * ks;
+          umma_ts(tmem + C::COL_V + 32 * (ks / per), a_hi, b_hi, idesc_f, (ks % per) ? 1u : 0u);
+          umma_ts(tmem + C::COL_VC, a_hi, b_lo, idesc_f, ks ? 1u : 0u);
+          const uint64_t a_lo = umma_desc_k(clo_addr + (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u);
+          umma_ss(tmem + C::COL_VC, a_lo, b_hi, idesc_f, 1u);
+        }
+        umma_commit(bar_v);
+        // ---- phase B once phase Q has written dL/dv: dC += Q_hi . A_hi^T + Q_hi . A_lo^T + Q_lo . A_hi^T
+        tc_wait(bar_q, j & 1, p.dbg, 2, j);
+        tc_fence_after();
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t b_hi = umma_desc_k(sbase + 2u * sub_bytes + (uint32_t)ks * 32u);
+          const uint64_t b_lo = umma_desc_k(sbase + 3u * sub_bytes + (uint32_t)ks * 32u);
+          umma_ts(tmem + C::COL_DC, tmem + C::COL_V + 8 * ks, b_hi, idesc_b, dc_accum);
+          dc_accum = 1u;
+          umma_ts(tmem + C::COL_DC, tmem + C::COL_V + 8 * ks, b_lo, idesc_b, 1u);
+          umma_ts(tmem + C::COL_DC, tmem + C::COL_QLO + 8 * ks, b_hi, idesc_b, 1u);
+        }
+        umma_commit(&bar_free[sg]);
+        if (j + 2 < ntiles) {  // refill this stage once its phase B has retired
+          tc_wait(&bar_free[sg], (j >> 1) & 1, p.dbg, 3, j);
+          mbar_expect_tx(&bar_full[sg], stage_bytes);
+          bulk_g2s(stage0 + sg * C::STAGE_BYTES, Abase + (size_t)(j + 2) * kpt * 4 * 32, stage_bytes, &bar_full[sg]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =====================================================================================================================
+    // phase-Q warps
+    // =====================================================================================================================
+    const int nks = kpt / 8;
+    const int per = (nks + 3) / 4;
+    const int npart = (nks + per - 1) / per;
+    const int cbase = 16 * half;        // this warp's columns of the tile
+    const int mycol = cbase + 8 * part; // the 8 channels this thread does the arithmetic for
+    const ClassSlot cs = s_cs[s];
+    const int2 an = s_ant[s];
+    float loss_acc = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      // this tile's inputs first: their latency hides behind the wait for phase F
+      const int f0 = (mt.j0 + j) * C::FT + mycol;
+      float4 in[7][2];
+      if (valid) {
+        const int o = cs.bl0 * p.nfp + f0, o0 = an.x + f0, o1 = an.y + f0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          in[0][h] = *reinterpret_cast<const float4*>(p.d_r + o + 4 * h);
+          in[1][h] = *reinterpret_cast<const float4*>(p.d_i + o + 4 * h);
+          in[2][h] = *reinterpret_cast<const float4*>(p.w + o + 4 * h);
+          in[3][h] = *reinterpret_cast<const float4*>(g_r + o0 + 4 * h);
+          in[4][h] = *reinterpret_cast<const float4*>(g_i + o0 + 4 * h);
+          in[5][h] = *reinterpret_cast<const float4*>(g_r + o1 + 4 * h);
+          in[6][h] = *reinterpret_cast<const float4*>(g_i + o1 + 4 * h);
+        }
+      }
+      tc_wait(bar_v, j & 1, p.dbg, 4, j);
+      tc_fence_after();
+      // V row of this thread, 16 columns: partial accumulators + the small terms, added with round-to-nearest
+      float v[16], t[16];
+      tmem_ld16(tmem + tlane + C::COL_V + cbase, v);
+      tmem_ld_wait();
+      for (int pa = 1; pa < npart; ++pa) {
+        tmem_ld16(tmem + tlane + C::COL_V + 32 * pa + cbase, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[i];
+      }
+      tmem_ld16(tmem + tlane + C::COL_VC + cbase, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += t[i];
+      // pair re / im: lane 2g holds v_r of group g, lane 2g + 1 its v_i; each takes 8 of the 16 channels
+      float vr[8], vi[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float send = part ? v[i] : v[8 + i];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        vr[i] = part ? recv : v[i];
+        vi[i] = part ? v[8 + i] : recv;
+      }
+      float qr[8], qi[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qr[i] = qi[i] = 0.f;
+      if (valid) {
+        const float* dr = reinterpret_cast<const float*>(&in[0][0]);
+        const float* di = reinterpret_cast<const float*>(&in[1][0]);
+        const float* ww = reinterpret_cast<const float*>(&in[2][0]);
+        const float* gr0 = reinterpret_cast<const float*>(&in[3][0]);
+        const float* gi0 = reinterpret_cast<const float*>(&in[4][0]);
+        const float* gr1 = reinterpret_cast<const float*>(&in[5][0]);
+        const float* gi1 = reinterpret_cast<const float*>(&in[6][0]);
+        float2 zz[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // calibration.py:1593-1609, as in the other kernels
+          const float P = gr0[i] * gr1[i] + gi0[i] * gi1[i];
+          const float Q = gr0[i] * gi1[i] - gi0[i] * gr1[i];
+          const float mr = P * vr[i] + Q * vi[i];
+          const float mi = P * vi[i] - Q * vr[i];
+          const float rr = dr[i] - mr, ri = di[i] - mi;
+          loss_acc += (rr * rr + ri * ri) * ww[i];
+          const float er = -2.f * ww[i] * rr, ei = -2.f * ww[i] * ri;
+          zz[i] = make_float2(er * vr[i] + ei * vi[i], er * vi[i] - ei * vr[i]);
+          qr[i] = P * er - Q * ei;
+          qi[i] = Q * er + P * ei;
+        }
+        float4* zdst = reinterpret_cast<float4*>(p.z + (size_t)(cs.bl0 * p.nfp + f0));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) zdst[i] = make_float4(zz[2 * i].x, zz[2 * i].y, zz[2 * i + 1].x, zz[2 * i + 1].y);
+      }
+      // back to rows: lane 2g needs q_r of all 16 columns, lane 2g + 1 q_i
+      float row[16], hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float send = part ? qr[i] : qi[i];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        row[i] = part ? recv : qr[i];
+        row[8 + i] = part ? qi[i] : recv;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        hi[i] = tf32_trunc(row[i]);
+        lo[i] = row[i] - hi[i];
+      }
+      tmem_st16(tmem + tlane + C::COL_V + cbase, hi);   // over the first partial accumulator: V has been read by every warp of
+      tmem_st16(tmem + tlane + C::COL_QLO + cbase, lo); // this quadrant's lanes that touches these columns (this warp itself)
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_plain(bar_q);
+    }
+    // ---- backward sums: wait for the last phase B, then row m of dC -> dcpart
+    {
+      const int last = ntiles - 1;
+      tc_wait(&bar_free[last & 1], (last >> 1) & 1, p.dbg, 5, last);
+      tc_fence_after();
+      float* dst = p.dcpart + (size_t)mt.seg * p.dc_plane + (size_t)cs.row0 * 2 + part;
+      const int k_lo = half * (kpt / 2), k_hi = k_lo + kpt / 2;
+      for (int k0 = k_lo; k0 < k_hi; k0 += 8) {
+        float d8[8];
+        tmem_ld8(tmem + tlane + C::COL_DC + k0, d8);  // .sync.aligned: the whole warp, also the lanes of missing groups
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (k0 + i < mt.ncomp) dst[(size_t)(k0 + i) * 2] = d8[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+    if (lane == 0) red[warp] = loss_acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0;
+    for (int w8 = 0; w8 < 8; ++w8) a += (double)red[w8];
+    double* dst = p.partials + (size_t)blockIdx.x * 4;
+    dst[0] = a;
+    dst[1] = 0.0;
+    dst[2] = 0.0;
+  }
+  if (mma_warp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace calb2

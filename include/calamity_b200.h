@@ -146,6 +146,8 @@ typedef struct {
   int64_t n_a_class;      /* basis floats resident for the classes (each distinct basis once) */
   int64_t n_a_class_nz;   /* basis elements those groups count for in n_a_nz (what a per-group copy would hold) */
   int64_t class_fma;      /* fused multiply-adds of the shared-basis kernel per iteration: 4 * n_a_class_nz */
+  int64_t n_tc_ctas;      /* CTAs of the tensor-core shape (tcgen05, classes of <= 128 vectors); 0 = off (CALB2_TC=0) */
+  int64_t n_tc_slots;     /* groups it fits */
 } calb2_plan_info;
 
 const char* calb2_last_error(void);
@@ -158,6 +160,9 @@ int calb2_device_count(int32_t* count);
  * library carries 256 pattern bytes on either side; this call counts the live allocations on the current device and the
  * guard zones a kernel has written into.  (compute-sanitizer is not available on the GPU pool this was developed on.) */
 int calb2_debug_check_guards(int64_t* nbuffers, int64_t* nviolations);
+/* Development aid: the 16-word progress / time-out record of the tensor-core kernel (mapped host memory; readable while
+ * another thread is blocked in a CUDA call). */
+int calb2_debug_tc_record(uint32_t* out16);
 
 /* Once per calibrate_and_model_tensor call: mirrors calibration.py:1143-1152. */
 int calb2_plan_create(const calb2_plan_desc* desc, calb2_plan** out);
