@@ -15,12 +15,14 @@
 //                                                             all tiles of the CTA
 //
 // The tensor core accumulates in float32 with truncation (measured: tools/tc_probe.cu, profiles/round2_tcgen05_probe.log: 26
-// chained accumulations cost 6e-7 relative).  V therefore goes to FOUR partial accumulators (a quarter of the k-steps each)
-// plus one for the two small split terms, and the five are added in registers with round-to-nearest.
+// chained accumulations cost 6e-7 relative).  V therefore goes to TWO partial accumulators (half of the k-steps each) plus one
+// for the two small split terms, and the three are added in registers with round-to-nearest.
 //
 // One warp issues the MMAs and the bulk copies (one thread), eight warps do phase Q; mbarriers connect them:
 //   full[s]  tile landed (TMA)            -> MMA warp          free[s]  phase B of the tile in stage s retired (tcgen05.commit) -> MMA warp refills s
-//   bar_v    phase F retired (commit)     -> phase-Q warps     bar_q    phase Q done (256 arrivals)                             -> MMA warp issues B
+//   v[b]     phase F retired (commit)     -> phase-Q warps     bar_q    phase Q done (256 arrivals)                             -> MMA warp issues B
+// Issue order of the MMA thread: F(0); then per tile j: F(j + 1) | wait Q(j) | B(j) | refill -- the tensor pipe executes in
+// issue order, so B(j) reads dL/dv(j) out of V buffer j & 1 before F(j + 2) overwrites it.
 // Descriptor encodings follow cute/arch/mma_sm100_desc.hpp; every operand form used here is checked by tools/tc_probe.cu.
 #pragma once
 #include "calfit_shared.cuh"
@@ -32,21 +34,27 @@ struct TcCfg {
   static constexpr int KPMAX = 128;                          // rows per class tile (ncomp rounded up to 16)
   static constexpr int NEPI = 256;                           // 8 phase-Q warps: TMEM lane quadrant = warp & 3, column half = warp >> 2
   static constexpr int NTHR = NEPI + 32;                     // + the MMA / TMA warp
-  static constexpr int STAGE_BYTES = 4 * KPMAX * 128;        // [b32 hi | b32 lo | std hi | std lo], 64 KB
+  static constexpr int STAGE_BYTES = 4 * KPMAX * 128;        // [b32 hi | b32 lo | std hi | std lo], 64 KB; the two halves are
+                                                             // separate rings: the MN-major pair is free again once phase F
+                                                             // retired, the K-major pair only after phase B
   static constexpr int OFF_STAGE = 0;
   static constexpr int OFF_CLO = 2 * STAGE_BYTES;            // C lo: [kp / 32 chunks][128 rows][128 B], K-major SWIZZLE_128B
   static constexpr int OFF_CS = OFF_CLO + (KPMAX / 32) * 128 * 128;
   static constexpr int OFF_ANT = OFF_CS + MS * 16;
   static constexpr int OFF_RED = OFF_ANT + MS * 8;
-  static constexpr int OFF_BAR = OFF_RED + 8 * 16;           // full[2], free[2], v, q
-  static constexpr int OFF_TMEM = OFF_BAR + 6 * 8;
+  static constexpr int OFF_BAR = OFF_RED + 8 * 16;           // full_f[2], full_b[2], free[2], v[2], q[2]
+  static constexpr int OFF_TMEM = OFF_BAR + 10 * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM + 16;
   // TMEM columns (512 allocated)
   static constexpr int COL_CHI = 0;     // C hi, 128
   static constexpr int COL_DC = 128;    // dC accumulator, 128
-  static constexpr int COL_V = 256;     // 4 partial V accumulators of 32; dL/dv hi is written over the first
-  static constexpr int COL_VC = 384;    // accumulator of the two small split terms
-  static constexpr int COL_QLO = 416;   // dL/dv lo
+  // two V buffers (tile parity) so that phase F of tile j + 1 runs on the tensor cores while phase Q of tile j runs on the CUDA
+  // cores: [partial 0 | partial 1 | small split terms], 32 columns each; dL/dv hi is written over partial 0 of its own buffer
+  static constexpr int COL_V = 256;
+  static constexpr int V_STRIDE = 96;
+  static constexpr int V_SMALL = 64;    // offset of the small-term accumulator inside a V buffer
+  static constexpr int COL_QLO = 448;   // dL/dv lo, two buffers of 32
+  static constexpr int NPART = 2;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -201,14 +209,14 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   int2* s_ant = reinterpret_cast<int2*>(smem + C::OFF_ANT);
   float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t *bar_full = bars, *bar_free = bars + 2, *bar_v = bars + 4, *bar_q = bars + 5;
+  uint64_t *bar_full = bars, *bar_fullb = bars + 2, *bar_free = bars + 4, *bar_v = bars + 6, *bar_q = bars + 8;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kpt = mt.kp, nslots = mt.nslots;
   const int ntiles = mt.j1 - mt.j0;
   const uint32_t sub_bytes = (uint32_t)kpt * 128u;       // one of the four copies of a tile
-  const uint32_t stage_bytes = 4u * sub_bytes;
+  const uint32_t half_bytes = 2u * sub_bytes;            // the MN-major pair / the K-major pair
   const float* Abase = p.At + mt.a_off + (size_t)mt.j0 * kpt * 4 * 32;
   const bool mma_warp = warp == 8;
 
@@ -216,18 +224,17 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (lane == 0) {
-      mbar_init(&bar_full[0], 1);
-      mbar_init(&bar_full[1], 1);
-      mbar_init(&bar_free[0], 1);
-      mbar_init(&bar_free[1], 1);
-      mbar_init(bar_v, 1);
-      mbar_init(bar_q, C::NEPI);
+      for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);  // full_f, full_b, free, v
+      mbar_init(&bar_q[0], C::NEPI);  // two: a fast warp may arrive for tile j + 1 before a slow one has arrived for tile j
+      mbar_init(&bar_q[1], C::NEPI);
       mbar_fence_init();
-      mbar_expect_tx(&bar_full[0], stage_bytes);
-      bulk_g2s(stage0, Abase, stage_bytes, &bar_full[0]);
-      if (ntiles > 1) {
-        mbar_expect_tx(&bar_full[1], stage_bytes);
-        bulk_g2s(stage0 + C::STAGE_BYTES, Abase + (size_t)kpt * 4 * 32, stage_bytes, &bar_full[1]);
+      for (int jj = 0; jj < 2 && jj < ntiles; ++jj) {
+        unsigned char* sb = stage0 + jj * C::STAGE_BYTES;
+        const float* src = Abase + (size_t)jj * kpt * 4 * 32;
+        mbar_expect_tx(&bar_full[jj], half_bytes);
+        bulk_g2s(sb, src, half_bytes, &bar_full[jj]);
+        mbar_expect_tx(&bar_fullb[jj], half_bytes);
+        bulk_g2s(sb + half_bytes, src + 2 * kpt * 32, half_bytes, &bar_fullb[jj]);
       }
     }
   }
@@ -284,40 +291,71 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       const uint32_t idesc_b = umma_idesc_tf32(128, kpt, 0);
       const uint32_t clo_addr = smem_u32(Clo);
       const int nks = kpt / 8;
-      const int per = (nks + 3) / 4;  // k-steps per partial V accumulator
+      const int per = (nks + C::NPART - 1) / C::NPART;  // k-steps per partial V accumulator
       uint32_t dc_accum = 0;
+      // phase F of tile jj into V buffer jj & 1:  V_p += C_hi . A_hi ;  V_small += C_hi . A_lo + C_lo . A_hi
+      // descriptor bases per stage; inside the loops only the 14-bit start-address field moves (units of 16 bytes)
+      uint64_t d_f_hi[2], d_f_lo[2], d_b_hi[2], d_b_lo[2];
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        const uint32_t sbase = smem_u32(stage0 + sg * C::STAGE_BYTES);
+        d_f_hi[sg] = umma_desc_mn32(sbase);
+        d_f_lo[sg] = umma_desc_mn32(sbase + sub_bytes);
+        d_b_hi[sg] = umma_desc_k(sbase + 2u * sub_bytes);
+        d_b_lo[sg] = umma_desc_k(sbase + 3u * sub_bytes);
+      }
+      const uint64_t d_clo = umma_desc_k(clo_addr);
+      auto issue_f = [&](int jj) {
+        const int sg = jj & 1;
+        const uint32_t vcol = tmem + C::COL_V + C::V_STRIDE * sg;
+        tc_wait(&bar_full[sg], (jj >> 1) & 1, p.dbg, 1, jj);
+        tc_fence_after();
+        uint64_t b_hi = d_f_hi[sg], b_lo = d_f_lo[sg], a_lo = d_clo;
+        uint32_t a_hi = tmem + C::COL_CHI, vp = vcol;
+        int in_part = 0;
+        for (int ks = 0; ks < nks; ++ks) {
+          umma_ts(vp, a_hi, b_hi, idesc_f, in_part ? 1u : 0u);
+          umma_ts(vcol + C::V_SMALL, a_hi, b_lo, idesc_f, ks ? 1u : 0u);
+          umma_ss(vcol + C::V_SMALL, a_lo, b_hi, idesc_f, 1u);
+          b_hi += 64;   // 8 rows x 128 B = 1024 B
+          b_lo += 64;
+          a_hi += 8;
+          a_lo += ((ks & 3) == 3) ? (16384u - 96u) / 16u : 2u;  // next 32 B of the row, or the next 32-vector chunk
+          if (++in_part == per) {
+            in_part = 0;
+            vp += 32;
+          }
+        }
+        umma_commit(&bar_v[sg]);
+      };
+      issue_f(0);
       for (int j = 0; j < ntiles; ++j) {
         const int sg = j & 1;
-        const uint32_t sbase = smem_u32(stage0 + sg * C::STAGE_BYTES);
-        tc_wait(&bar_full[sg], (j >> 1) & 1, p.dbg, 1, j);
-        tc_fence_after();
-        // ---- phase F: V_p += C_hi . A_hi ; V_c += C_hi . A_lo + C_lo . A_hi
-        for (int ks = 0; ks < nks; ++ks) {
-          const uint64_t b_hi = umma_desc_mn32(sbase + (uint32_t)ks * 1024u);
-          const uint64_t b_lo = umma_desc_mn32(sbase + sub_bytes + (uint32_t)ks * 1024u);
-          const uint32_t a_hi = tmem + C::COL_CHI + 8 * ks;
-          umma_ts(tmem + C::COL_V + 32 * (ks / per), a_hi, b_hi, idesc_f, (ks % per) ? 1u : 0u);
-          umma_ts(tmem + C::COL_VC, a_hi, b_lo, idesc_f, ks ? 1u : 0u);
-          const uint64_t a_lo = umma_desc_k(clo_addr + (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u);
-          umma_ss(tmem + C::COL_VC, a_lo, b_hi, idesc_f, 1u);
+        unsigned char* sb = stage0 + sg * C::STAGE_BYTES;
+        if (j + 1 < ntiles) issue_f(j + 1);  // runs on the tensor cores while phase Q of tile j runs on the CUDA cores
+        if (j + 2 < ntiles) {  // phase F of tile j has retired: its MN-major pair can take tile j + 2 (a whole tile of lead time)
+          tc_wait(&bar_v[sg], (j >> 1) & 1, p.dbg, 6, j);
+          mbar_expect_tx(&bar_full[sg], half_bytes);
+          bulk_g2s(sb, Abase + (size_t)(j + 2) * kpt * 4 * 32, half_bytes, &bar_full[sg]);
         }
-        umma_commit(bar_v);
         // ---- phase B once phase Q has written dL/dv: dC += Q_hi . A_hi^T + Q_hi . A_lo^T + Q_lo . A_hi^T
-        tc_wait(bar_q, j & 1, p.dbg, 2, j);
+        tc_wait(&bar_q[sg], (j >> 1) & 1, p.dbg, 2, j);
+        tc_wait(&bar_fullb[sg], (j >> 1) & 1, p.dbg, 7, j);
         tc_fence_after();
+        const uint32_t qhi = tmem + C::COL_V + C::V_STRIDE * sg, qlo = tmem + C::COL_QLO + 32 * sg;
+#pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t b_hi = umma_desc_k(sbase + 2u * sub_bytes + (uint32_t)ks * 32u);
-          const uint64_t b_lo = umma_desc_k(sbase + 3u * sub_bytes + (uint32_t)ks * 32u);
-          umma_ts(tmem + C::COL_DC, tmem + C::COL_V + 8 * ks, b_hi, idesc_b, dc_accum);
+          const uint64_t b_hi = d_b_hi[sg] + 2 * ks, b_lo = d_b_lo[sg] + 2 * ks;  // 32 B along the 128 B row
+          umma_ts(tmem + C::COL_DC, qhi + 8 * ks, b_hi, idesc_b, dc_accum);
           dc_accum = 1u;
-          umma_ts(tmem + C::COL_DC, tmem + C::COL_V + 8 * ks, b_lo, idesc_b, 1u);
-          umma_ts(tmem + C::COL_DC, tmem + C::COL_QLO + 8 * ks, b_hi, idesc_b, 1u);
+          umma_ts(tmem + C::COL_DC, qhi + 8 * ks, b_lo, idesc_b, 1u);
+          umma_ts(tmem + C::COL_DC, qlo + 8 * ks, b_hi, idesc_b, 1u);
         }
         umma_commit(&bar_free[sg]);
-        if (j + 2 < ntiles) {  // refill this stage once its phase B has retired
+        if (j + 2 < ntiles) {  // the K-major pair is free once phase B has retired; tile j + 2 needs it two tiles from now
           tc_wait(&bar_free[sg], (j >> 1) & 1, p.dbg, 3, j);
-          mbar_expect_tx(&bar_full[sg], stage_bytes);
-          bulk_g2s(stage0 + sg * C::STAGE_BYTES, Abase + (size_t)(j + 2) * kpt * 4 * 32, stage_bytes, &bar_full[sg]);
+          mbar_expect_tx(&bar_fullb[sg], half_bytes);
+          bulk_g2s(sb + half_bytes, Abase + (size_t)(j + 2) * kpt * 4 * 32 + 2 * kpt * 32, half_bytes, &bar_fullb[sg]);
         }
       }
     }
@@ -327,44 +365,52 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
     // phase-Q warps
     // =====================================================================================================================
     const int nks = kpt / 8;
-    const int per = (nks + 3) / 4;
+    const int per = (nks + C::NPART - 1) / C::NPART;
     const int npart = (nks + per - 1) / per;
     const int cbase = 16 * half;        // this warp's columns of the tile
     const int mycol = cbase + 8 * part; // the 8 channels this thread does the arithmetic for
     const ClassSlot cs = s_cs[s];
     const int2 an = s_ant[s];
     float loss_acc = 0.f;
-    for (int j = 0; j < ntiles; ++j) {
-      // this tile's inputs first: their latency hides behind the wait for phase F
-      const int f0 = (mt.j0 + j) * C::FT + mycol;
-      float4 in[7][2];
-      if (valid) {
-        const int o = cs.bl0 * p.nfp + f0, o0 = an.x + f0, o1 = an.y + f0;
+    // this thread's inputs are loaded ONE TILE AHEAD (registers): their DRAM / L2 latency hides behind the previous tile's work
+    float4 in[7][2], nx[7][2];
+    auto load_inputs = [&](int jt, float4 (&dst)[7][2]) {
+      const int f0 = (mt.j0 + jt) * C::FT + mycol;
+      const int o = cs.bl0 * p.nfp + f0, o0 = an.x + f0, o1 = an.y + f0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          in[0][h] = *reinterpret_cast<const float4*>(p.d_r + o + 4 * h);
-          in[1][h] = *reinterpret_cast<const float4*>(p.d_i + o + 4 * h);
-          in[2][h] = *reinterpret_cast<const float4*>(p.w + o + 4 * h);
-          in[3][h] = *reinterpret_cast<const float4*>(g_r + o0 + 4 * h);
-          in[4][h] = *reinterpret_cast<const float4*>(g_i + o0 + 4 * h);
-          in[5][h] = *reinterpret_cast<const float4*>(g_r + o1 + 4 * h);
-          in[6][h] = *reinterpret_cast<const float4*>(g_i + o1 + 4 * h);
-        }
+      for (int h = 0; h < 2; ++h) {
+        dst[0][h] = *reinterpret_cast<const float4*>(p.d_r + o + 4 * h);
+        dst[1][h] = *reinterpret_cast<const float4*>(p.d_i + o + 4 * h);
+        dst[2][h] = *reinterpret_cast<const float4*>(p.w + o + 4 * h);
+        dst[3][h] = *reinterpret_cast<const float4*>(g_r + o0 + 4 * h);
+        dst[4][h] = *reinterpret_cast<const float4*>(g_i + o0 + 4 * h);
+        dst[5][h] = *reinterpret_cast<const float4*>(g_r + o1 + 4 * h);
+        dst[6][h] = *reinterpret_cast<const float4*>(g_i + o1 + 4 * h);
       }
-      tc_wait(bar_v, j & 1, p.dbg, 4, j);
+    };
+    if (valid) load_inputs(0, nx);
+    for (int j = 0; j < ntiles; ++j) {
+      const int f0 = (mt.j0 + j) * C::FT + mycol;
+      if (valid) {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+          in[a][0] = nx[a][0];
+          in[a][1] = nx[a][1];
+        }
+        if (j + 1 < ntiles) load_inputs(j + 1, nx);
+      }
+      const uint32_t vcol = tmem + tlane + C::COL_V + C::V_STRIDE * (j & 1) + cbase;
+      tc_wait(&bar_v[j & 1], (j >> 1) & 1, p.dbg, 4, j);
       tc_fence_after();
       // V row of this thread, 16 columns: partial accumulators + the small terms, added with round-to-nearest
       float v[16], t[16];
-      tmem_ld16(tmem + tlane + C::COL_V + cbase, v);
-      tmem_ld_wait();
-      for (int pa = 1; pa < npart; ++pa) {
-        tmem_ld16(tmem + tlane + C::COL_V + 32 * pa + cbase, t);
-        tmem_ld_wait();
+      tmem_ld16(vcol, v);
+      if (npart > 1) {
+        tmem_ld16(vcol + 32, t);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += t[i];
       }
-      tmem_ld16(tmem + tlane + C::COL_VC + cbase, t);
-      tmem_ld_wait();
+      tmem_ld16(vcol + C::V_SMALL, t);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] += t[i];
       // pair re / im: lane 2g holds v_r of group g, lane 2g + 1 its v_i; each takes 8 of the 16 channels
@@ -419,11 +465,11 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
         hi[i] = tf32_trunc(row[i]);
         lo[i] = row[i] - hi[i];
       }
-      tmem_st16(tmem + tlane + C::COL_V + cbase, hi);   // over the first partial accumulator: V has been read by every warp of
-      tmem_st16(tmem + tlane + C::COL_QLO + cbase, lo); // this quadrant's lanes that touches these columns (this warp itself)
+      tmem_st16(vcol, hi);  // over partial 0 of this tile's V buffer: these lanes / columns are read by this warp only
+      tmem_st16(tmem + tlane + C::COL_QLO + 32 * (j & 1) + cbase, lo);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive_plain(bar_q);
+      mbar_arrive_plain(&bar_q[j & 1]);
     }
     // ---- backward sums: wait for the last phase B, then row m of dC -> dcpart
     {

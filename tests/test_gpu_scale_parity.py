@@ -12,15 +12,25 @@ from tests.helpers import flat_from_synth, long_baseline_subset, mixed_problem, 
 
 pytestmark = pytest.mark.gpu
 F = np.float64
-# both device paths: the streaming kernel (one private basis copy per group) and the shared-basis kernel (each distinct
-# basis stored once; automatic for classes of >= 4 groups)
-PATHS = [pytest.param(dict(shared_basis=-1), id="stream"), pytest.param(dict(shared_basis=0), id="shared")]
+# the device paths: the streaming kernel (one private basis copy per group); the shared-basis path as shipped (each distinct
+# basis stored once, automatic for classes of >= 4 groups: classes of <= 128 vectors on the tensor cores, calfit_tc.cuh, the
+# rest on the CUDA-core shapes of calfit_shared.cuh); and the shared-basis path with the tensor-core shape switched off
+PATHS = [pytest.param(dict(shared_basis=-1), id="stream"), pytest.param(dict(shared_basis=0), id="shared"),
+         pytest.param(dict(shared_basis=0, tc=False), id="shared-cuda-cores")]
 
 
-def _plan(p, **kw):
+def _plan(p, tc=True, **kw):
+    import os
+
     from calamity_b200.fitter import FitPlan
 
-    plan = FitPlan(p.lay, device=0, **kw)
+    os.environ["CALB2_TC"] = "1" if tc else "0"  # read by calb2_plan_create
+    try:
+        plan = FitPlan(p.lay, device=0, **kw)
+    finally:
+        os.environ.pop("CALB2_TC", None)
+    if kw.get("shared_basis", 0) >= 0:
+        assert (plan.info["n_tc_ctas"] > 0) == tc
     plan.set_integration(p.data_r, p.data_i, p.wgts)
     plan.set_gains(p.g0_r, p.g0_i)
     plan.set_coeffs(p.c0_r, p.c0_i)
@@ -95,6 +105,7 @@ def test_hera128_full_loss_and_gradient(native_built, hera128, path):
     info = _check_loss_and_grads(flat_from_synth(hera128), plan_kw=path)
     assert info["nbls_total"] == 8128
     assert (info["n_class_slots"] > 8000) == (path["shared_basis"] == 0)
+    assert (info["n_tc_slots"] > 6000) == (path["shared_basis"] == 0 and path.get("tc", True))
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -108,6 +119,8 @@ def test_hera128_long_baseline_trajectory(native_built, hera128, reg, path):
 def test_hera350_full_loss_and_gradient(native_built, hera350, path):
     """The bench workload itself: 61 075 baselines x 1024 channels (26 GB of basis on the streaming path, 66 MB on the
     shared-basis path)."""
+    if "tc" in path:
+        pytest.skip("the CUDA-core shapes are covered at this size by the groups of > 128 vectors of the default path")
     info = _check_loss_and_grads(flat_from_synth(hera350), regs=(None,) if path["shared_basis"] < 0 else (None, "sum"),
                                  plan_kw=path)
     assert info["nbls_total"] == 61075

@@ -13,10 +13,16 @@ pytestmark = pytest.mark.gpu
 F = np.float64
 
 
-def _plan(p, **kw):
+def _plan(p, tc=True, **kw):
+    import os
+
     from calamity_b200.fitter import FitPlan
 
-    plan = FitPlan(p.lay, device=0, **kw)
+    os.environ["CALB2_TC"] = "1" if tc else "0"  # read by calb2_plan_create: tensor-core shape on (default) / off
+    try:
+        plan = FitPlan(p.lay, device=0, **kw)
+    finally:
+        os.environ.pop("CALB2_TC", None)
     plan.set_integration(p.data_r, p.data_i, p.wgts)
     plan.set_gains(p.g0_r, p.g0_i)
     plan.set_coeffs(p.c0_r, p.c0_i)
@@ -66,18 +72,21 @@ def _cases():
     yield "redundant", redundant_shared_problem(), 1
 
 
+@pytest.mark.parametrize("tc", [True, False], ids=["tensor-cores", "cuda-cores"])
 @pytest.mark.parametrize("reg", [None, "sum"])
-def test_loss_and_gradient_against_oracle(native_built, reg):
+def test_loss_and_gradient_against_oracle(native_built, reg, tc):
     for name, p, mode in _cases():
         rp = RaggedProblem(p.lay)
         pr = float(np.sum(p.data_r.astype(F) * p.wgts)) * 0.9
         pi = float(np.sum(p.data_i.astype(F) * p.wgts)) * 1.1
         ol, ogr, ogi, ocr, oci = rp.loss_and_grads(*_args64(p), regularization=reg, prior_r_sum=F(pr), prior_i_sum=F(pi))
-        plan = _plan(p, shared_basis=mode)
+        plan = _plan(p, tc=tc, shared_basis=mode)
         info = dict(plan.info)
         loss, dgr, dgi, dcr, dci = plan.loss_and_grads(model_regularization=reg, prior_r_sum=pr, prior_i_sum=pi)
         plan.close()
         assert info["n_class_slots"] > 0, name
+        # the tensor-core shape takes single-baseline classes of <= 128 vectors ('redundant' has multi-baseline slots)
+        assert (info["n_tc_slots"] > 0) == (tc and name != "redundant"), (name, info["n_tc_slots"])
         if mode == 1 and name != "redundant":
             assert info["n_class_slots"] == info["nslots_total"] and info["nitems"] == 0, name
         errs = (abs(float(loss) - float(ol)) / abs(float(ol)), rel_err(dgr, ogr), rel_err(dgi, ogi), rel_err(dcr, ocr),
@@ -88,8 +97,9 @@ def test_loss_and_gradient_against_oracle(native_built, reg):
         assert max(errs[1:]) < 1e-4, name
 
 
+@pytest.mark.parametrize("tc", [True, False], ids=["tensor-cores", "cuda-cores"])
 @pytest.mark.parametrize("optimizer,reg", [("Adamax", None), ("Adamax", "sum"), ("Adam", "sum")])
-def test_fit_trajectory_against_oracle(native_built, optimizer, reg):
+def test_fit_trajectory_against_oracle(native_built, optimizer, reg, tc):
     nsteps = 60
     for name, p, mode in list(_cases())[1:]:
         if name == "redundant":  # random data: scale the step so the loss falls smoothly
@@ -102,7 +112,7 @@ def test_fit_trajectory_against_oracle(native_built, optimizer, reg):
         kw = dict(optimizer=optimizer, maxsteps=nsteps, tol=0.0, learning_rate=lr, model_regularization=reg)
         o = rp.fit(p.g0_r, p.g0_i, p.c0_r, p.c0_i, p.data_r, p.data_i, p.wgts, prior_r_sum=F(np.float32(pr)),
                    prior_i_sum=F(np.float32(pi)), **kw)
-        plan = _plan(p, shared_basis=mode)
+        plan = _plan(p, tc=tc, shared_basis=mode)
         hist, res = plan.fit(prior_r_sum=pr, prior_i_sum=pi, **kw)
         g_r, g_i = plan.get_gains()
         c_r, c_i = plan.get_coeffs()

@@ -216,6 +216,51 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const Params p) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// Cycles per tcgen05.mma (issue to retire, `reps` back to back): form 0 = TS, B MN-major N=32; 1 = SS (A K-major), B MN-major N=32;
+// 2 = TS, B K-major N=n; 3 = TS, B MN-major N=64 (two 32-column blocks, LBO)
+__global__ void __launch_bounds__(128, 1) time_kernel(int form, int n, int reps, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = tid; e < 40960; e += 128) reinterpret_cast<float*>(smem)[e] = 0.001f * (e & 15);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) {
+    const uint32_t sb = smem_u32(smem);
+    const uint64_t b_mn = smem_desc(sb, 8192, 512, 1), b_k = smem_desc_sw128(sb, 16, 1024), a_k = smem_desc_sw128(sb + 65536, 16, 1024);
+    const uint32_t id32 = idesc_tf32(128, 32, 0, 1), id64 = idesc_tf32(128, 64, 0, 1), idn = idesc_tf32(128, n, 0, 0);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (form == 0) mma_ts(tmem + 256, tmem + (r & 15) * 8, b_mn + (uint64_t)((r & 7) * 64), id32, 1);
+      else if (form == 1) mma_ss(tmem + 256, a_k + (uint64_t)((r & 3) * 2), b_mn + (uint64_t)((r & 7) * 64), id32, 1);
+      else if (form == 2) mma_ts(tmem + 256, tmem + (r & 3) * 8, b_k + (uint64_t)((r & 3) * 2), idn, 1);
+      else mma_ts(tmem + 256, tmem + (r & 15) * 8, b_mn + (uint64_t)((r & 7) * 64), id64, 1);
+    }
+    const long long t1 = clock64();
+    mma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  __syncthreads();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 static float tf32_trunc(float x) {
   uint32_t u;
   memcpy(&u, &x, 4);
@@ -293,6 +338,24 @@ int main() {
     cudaFree(dA);
     cudaFree(dB);
     cudaFree(dD);
+  }
+  {
+    long long* dout;
+    CK(cudaMalloc(&dout, 16));
+    CK(cudaFuncSetAttribute(time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180224));
+    struct TCase { int form, n; const char* name; };
+    const TCase tcs[] = {{0, 32, "TS  B MN-major  N=32"}, {1, 32, "SS  B MN-major  N=32"}, {3, 64, "TS  B MN-major  N=64"},
+                         {2, 16, "TS  B K-major   N=16"}, {2, 64, "TS  B K-major   N=64"}, {2, 128, "TS  B K-major   N=128"}};
+    for (const TCase& tc : tcs)
+      for (int reps : {64, 512}) {
+        time_kernel<<<1, 128, 180224>>>(tc.form, tc.n, reps, dout);
+        CK(cudaDeviceSynchronize());
+        long long h[2];
+        CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));
+        printf("timing %-22s reps %4d: issue %6.1f cyc/MMA, issue->retire %6.1f cyc/MMA\n", tc.name, reps, (double)h[0] / reps,
+               (double)h[1] / reps);
+      }
+    cudaFree(dout);
   }
   printf("%s\n", bad ? "PROBE FAILED" : "PROBE PASSED");
   return bad ? 1 : 0;
