@@ -59,6 +59,7 @@ class FitOptions(C.Structure):
         ("l2_regularization_strength", C.c_double),
         ("learning_rate_power", C.c_double),
         ("nesterov", C.c_int32),
+        ("weight_decay", C.c_double),
     ]
 
 
@@ -112,6 +113,7 @@ _SIGNATURES = {
     "calb2_plan_destroy": (C.c_int, [C.c_void_p]),
     "calb2_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),
     "calb2_plan_set_basis": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "calb2_plan_set_variables": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "calb2_set_integration": (C.c_int, [C.c_void_p, _FP, _FP, _FP]),
     "calb2_set_gains": (C.c_int, [C.c_void_p, _FP, _FP]),
     "calb2_set_coeffs": (C.c_int, [C.c_void_p, _FP, _FP]),

@@ -237,6 +237,12 @@ struct calb2_plan {
   unsigned long long xtimeout_ns = 20000000000ull;  // bound on every wait for a peer's flag (CALB2_PEER_TIMEOUT_MS)
   bool peers_open = false;
   DevBuf<unsigned int> tail_counter;
+  // LAMB (per-variable trust ratios): coefficient ranges of the reference's chunk variables, norm partials, ratios
+  std::vector<long long> var_bounds;
+  bool var_uploaded = false;
+  DevBuf<long long> d_var_bounds;
+  DevBuf<double> lamb_gain_partials, lamb_coef_partials;
+  DevBuf<float> lamb_ratio;
   // the coefficient update runs on a second stream next to the gain update (they touch disjoint state)
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -568,8 +574,12 @@ static GainsParams gains_params(calb2_plan* pl, const FitState* st, const FitCon
   gp.st = st;
   gp.k = k;
   gp.nfp = pl->nfp;
+  gp.nf = pl->nf;
   gp.nants = pl->nants;
   gp.mode = mode;
+  gp.lamb.gain_partials = pl->lamb_gain_partials.p;
+  gp.lamb.coef_partials = pl->lamb_coef_partials.p;
+  gp.lamb.ratio = pl->lamb_ratio.p;
   gp.sum = sum ? 1 : 0;
   gp.eval = eval;
   gp.peers.n = 0;
@@ -604,6 +614,9 @@ static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitCon
   cp.plane = pl->dc_plane;
   cp.first_class_row = pl->first_class_row;
   cp.mode = mode;
+  cp.var_bounds = pl->d_var_bounds.p;
+  cp.nvar = (int)pl->var_bounds.size() - 1;
+  cp.lamb_ratio = pl->lamb_ratio.p;
   return cp;
 }
 
@@ -614,6 +627,21 @@ static int ensure_use_min_buffers(calb2_plan* pl) {
     if (int r = dalloc(pl->csnap_r, (size_t)pl->ncoef, pl)) return r;
     if (int r = dalloc(pl->csnap_i, (size_t)pl->ncoef, pl)) return r;
   }
+  return 0;
+}
+static int ensure_lamb_buffers(calb2_plan* pl) {
+  if (pl->var_bounds.empty()) pl->var_bounds = {0ll, (long long)pl->ncoef};
+  const size_t nvar = pl->var_bounds.size() - 1;
+  if (!pl->var_uploaded) {
+    if (int r = dalloc(pl->d_var_bounds, nvar + 1, pl)) return r;
+    CU(cudaMemcpyAsync(pl->d_var_bounds.p, pl->var_bounds.data(), (nvar + 1) * sizeof(long long), cudaMemcpyHostToDevice, pl->stream));
+    CU(cudaStreamSynchronize(pl->stream));
+    if (int r = dalloc(pl->lamb_coef_partials, nvar * LAMB_SPLIT * 4, pl)) return r;
+    if (int r = dalloc(pl->lamb_ratio, 2 + 2 * nvar, pl)) return r;
+    pl->var_uploaded = true;
+  }
+  if (!pl->lamb_gain_partials.p)
+    if (int r = dalloc(pl->lamb_gain_partials, (size_t)pl->nants * ((pl->nfp + GK_CH - 1) / GK_CH) * 4, pl)) return r;
   return 0;
 }
 static int ensure_sum_buffers(calb2_plan* pl) {
@@ -871,9 +899,48 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     fp.nitems = npartials;
     finalize_kernel<<<1, 1024, 0, pl->stream>>>(fp);
     CU(cudaGetLastError());
-    if (int r = fork_coeffs()) return r;
-    gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 0, sum, 0));
-    CU(cudaGetLastError());
+    if (k.optimizer == CALB2_OPT_LAMB) {
+      // pass 1: moments everywhere + norm partials; trust ratio per variable; pass 2: apply.  One stream, seven launches.
+      const unsigned cgrid = (unsigned)((pl->ncoef + 255) / 256);
+      const int nvar = freeze ? 0 : (int)pl->var_bounds.size() - 1;
+      gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 5, sum, 0));
+      CU(cudaGetLastError());
+      if (!freeze) {
+        coeffs_kernel<<<cgrid, 256, 0, pl->stream>>>(coeff_params(pl, pl->state.p, k, 5, sum));
+        CU(cudaGetLastError());
+        LambNormParams np{};
+        np.c_r = pl->c_r.p;
+        np.c_i = pl->c_i.p;
+        np.m_r = pl->cm_r.p;
+        np.u_r = pl->cu_r.p;
+        np.m_i = pl->cm_i.p;
+        np.u_i = pl->cu_i.p;
+        np.var_bounds = pl->d_var_bounds.p;
+        np.partials = pl->lamb_coef_partials.p;
+        np.st = pl->state.p;
+        np.k = k;
+        lamb_coef_norm_kernel<<<dim3((unsigned)nvar, LAMB_SPLIT), 256, 0, pl->stream>>>(np);
+        CU(cudaGetLastError());
+      }
+      LambRatioParams rp{};
+      rp.gain_partials = pl->lamb_gain_partials.p;
+      rp.n_gain_partials = (int)(ggrid.x * ggrid.y);
+      rp.coef_partials = pl->lamb_coef_partials.p;
+      rp.ratio = pl->lamb_ratio.p;
+      lamb_ratio_kernel<<<1 + nvar, 32, 0, pl->stream>>>(rp);
+      CU(cudaGetLastError());
+      gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 6, sum, 0));
+      CU(cudaGetLastError());
+      if (!freeze) {
+        coeffs_kernel<<<cgrid, 256, 0, pl->stream>>>(coeff_params(pl, pl->state.p, k, 6, sum));
+        CU(cudaGetLastError());
+      }
+      *launches += freeze ? 1 : 4;
+    } else {
+      if (int r = fork_coeffs()) return r;
+      gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 0, sum, 0));
+      CU(cudaGetLastError());
+    }
   }
   if (forked) CU(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));  // join: the next step reads the new coefficients
   CALB2_STAGE()
@@ -1899,9 +1966,22 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, double prior_r,
   return 0;
 }
 
+int calb2_plan_set_variables(calb2_plan* pl, int32_t nvars, const int64_t* coef_bounds) {
+  if (!pl || nvars < 1 || !coef_bounds) return fail(CALB2_ERR_ARG, "null argument or no variables");
+  const long long ncoef = (long long)pl->ncoef;
+  if (coef_bounds[0] != 0 || coef_bounds[nvars] != ncoef) return fail(CALB2_ERR_ARG, "coef_bounds must run from 0 to n_c_nz = %lld", ncoef);
+  for (int v = 0; v < nvars; ++v)
+    if (coef_bounds[v + 1] <= coef_bounds[v]) return fail(CALB2_ERR_ARG, "coef_bounds must be strictly ascending (variable %d)", v);
+  if (pl->gen) return 0;  // the generic path has no optimizer that uses them
+  pl->var_bounds.assign(coef_bounds, coef_bounds + nvars + 1);
+  pl->var_uploaded = false;
+  return 0;
+}
+
 int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, calb2_fit_result* res) {
   if (!pl || !o || !res) return fail(CALB2_ERR_ARG, "null argument");
   if (pl->gen) {
+    if (o->optimizer == CALB2_OPT_LAMB) return fail(CALB2_ERR_UNSUPPORTED, "LAMB runs on float32 plans only");
     if (o->optimizer < 0 || o->optimizer > CALB2_OPT_FTRL) return fail(CALB2_ERR_ARG, "unknown optimizer id %d", o->optimizer);
     if (o->maxsteps < 0 || o->n_profile_steps < 0) return fail(CALB2_ERR_ARG, "negative step count");
     if (o->maxsteps > 0 && !loss_history_v) return fail(CALB2_ERR_ARG, "loss_history is null");
@@ -1910,10 +1990,14 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
   }
   float* loss_history = (float*)loss_history_v;
   if (!pl->have_data || !pl->have_gains || !pl->have_coeffs) return fail(CALB2_ERR_STATE, "integration, gains and coefficients must be set first");
-  if (o->optimizer < 0 || o->optimizer > CALB2_OPT_FTRL) return fail(CALB2_ERR_ARG, "unknown optimizer id %d", o->optimizer);
+  if (o->optimizer < 0 || o->optimizer > CALB2_OPT_LAMB) return fail(CALB2_ERR_ARG, "unknown optimizer id %d", o->optimizer);
+  if (o->optimizer == CALB2_OPT_LAMB && pl->nranks > 1)
+    return fail(CALB2_ERR_UNSUPPORTED, "LAMB's per-variable norms are not exchanged between ranks: single-GPU plans only");
   if (o->maxsteps < 0 || o->n_profile_steps < 0) return fail(CALB2_ERR_ARG, "negative step count");
   if (o->maxsteps > 0 && !loss_history) return fail(CALB2_ERR_ARG, "loss_history is null");
   CU(cudaSetDevice(pl->device));
+  if (o->optimizer == CALB2_OPT_LAMB)
+    if (int r = ensure_lamb_buffers(pl)) return r;
   const bool sum = o->regularization == CALB2_REG_SUM;
   const bool freeze = o->freeze_model != 0;
   if (sum)
@@ -1935,6 +2019,7 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
   k.l2 = (float)o->l2_regularization_strength;
   k.lr_power = (float)o->learning_rate_power;
   k.nesterov = o->nesterov;
+  k.weight_decay = (float)o->weight_decay;
   k.maxsteps = o->maxsteps;
   k.tol = o->tol;
   k.use_min = o->use_min;

@@ -56,6 +56,7 @@ struct FitConsts {
   int optimizer;     // CALB2_OPT_*
   float lr, beta1, beta2, eps;
   float rho, momentum, init_acc, l1, l2, lr_power;  // RMSprop / Adadelta / SGD / Adagrad / Ftrl (Keras names)
+  float weight_decay;                               // LAMB (tensorflow_addons)
   int nesterov;
   int maxsteps;
   double tol;
@@ -250,7 +251,7 @@ __device__ __forceinline__ void axpy4(float c, const float4& a, float4& v) {
 // optimizer rules (Keras OptimizerV2; see oracle/restatement.py for provenance)
 //   SPARSE = the IndexedSlices form used for the gains, dense form for the coefficients
 // ------------------------------------------------------------------------------------------------
-enum { OPT_ADAMAX = 0, OPT_ADAM = 1, OPT_SGD = 2, OPT_RMSPROP = 3, OPT_ADAGRAD = 4, OPT_ADADELTA = 5, OPT_NADAM = 6, OPT_FTRL = 7 };
+enum { OPT_ADAMAX = 0, OPT_ADAM = 1, OPT_SGD = 2, OPT_RMSPROP = 3, OPT_ADAGRAD = 4, OPT_ADADELTA = 5, OPT_NADAM = 6, OPT_FTRL = 7, OPT_LAMB = 8 };
 
 // float / double overloads so the optimizer rules below are written once for both precisions
 __device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
@@ -323,6 +324,29 @@ __device__ __forceinline__ T opt_step(const K& k, const S* st, T theta, T g, T& 
     }
   }
 }
+
+// tensorflow_addons LAMB (calibration.py:15, 26; tfa.optimizers.LAMB._resource_apply_dense): Adam moments with bias correction,
+// update = m_hat / (sqrt(v_hat) + eps) + weight_decay * theta, then theta -= lr * ratio * update with ONE trust ratio
+// ||theta|| / ||update|| per variable (g_r, g_i, every chunk's fg_r / fg_i tensor).  Two passes: lamb_moments() updates the
+// moments and returns the update (its square and theta's are summed per variable by the callers, fixed order), lamb_update()
+// recomputes the update from the stored moments.  st->aux[0] = 1 - beta_1^t, st->aux[1] = 1 - beta_2^t.
+template <class K, class S>
+__device__ __forceinline__ float lamb_update(const K& k, const S* st, float theta, float m, float u) {
+  return (m / st->aux[0]) / (sqrtf(u / st->aux[1]) + k.eps) + k.weight_decay * theta;
+}
+template <class K, class S>
+__device__ __forceinline__ float lamb_moments(const K& k, const S* st, float theta, float g, float& m, float& u) {
+  m = m * k.beta1 + g * (1.f - k.beta1);
+  u = u * k.beta2 + (g * g) * (1.f - k.beta2);
+  return lamb_update(k, st, theta, m, u);
+}
+struct LambVars {
+  // partial sums (theta^2, update^2) per CTA: the gain kernel's CTAs hold g_r in [0], [1] and g_i in [2], [3]; the coefficient
+  // kernel's CTAs of chunk c (its own launch) likewise for fg_r[c] / fg_i[c]
+  double* gain_partials;   // [gain CTAs][4]
+  double* coef_partials;   // [coefficient CTAs][4]
+  float* ratio;            // [2 + 2 nchunks]: g_r, g_i, then (fg_r[c], fg_i[c]) per chunk
+};
 
 // Keras local_step = iterations + 1; powers evaluated in double and rounded once (identical in every kernel)
 template <class T, class K>
@@ -900,6 +924,10 @@ __global__ void __launch_bounds__(1024, 1) finalize_kernel(const FinalizeParams 
   const int t = st->step;
   st->lr_t = bias_corrected_lr(p.k, t);
   if (p.k.optimizer == OPT_NADAM) nadam_schedule<float>(p.k, st, t);
+  if (p.k.optimizer == OPT_LAMB) {
+    st->aux[0] = 1.f - (float)pow((double)p.k.beta1, (double)(t + 1));
+    st->aux[1] = 1.f - (float)pow((double)p.k.beta2, (double)(t + 1));
+  }
   int snap = 0;
   const int rec = t - p.k.n_skip;
   if (rec >= 0) {
@@ -941,7 +969,10 @@ struct GainsParams {
   FitConsts k;
   int nfp;
   int nants;
-  int mode;             // 0: reduce + update; 1: reduce only -> grad; 2: update only from grad; 4: as 1, before finalize
+  int mode;             // 0: reduce + update; 1: reduce only -> grad; 2: update only from grad; 4: as 1, before finalize;
+                        // 5: LAMB pass 1 (reduce, moments, per-CTA norm partials); 6: LAMB pass 2 (apply with the trust ratios)
+  int nf;               // channels that exist (the padding up to nfp takes no part in LAMB's norms)
+  LambVars lamb;
   int sum;
   int eval;             // 1: stand-alone gradient evaluation (no step in flight)
   PeerView peers;       // mode 2 with peers.n > 1: gradient = sum over ranks (rank order) of their published partials
@@ -989,7 +1020,7 @@ __global__ void __launch_bounds__(GK_THREADS) gains_kernel(const GainsParams p) 
   const float* __restrict__ gi = p.g_i[src];
   const size_t o = (size_t)ant * p.nfp + f;
   float2 acc_r = make_float2(0.f, 0.f), acc_i = make_float2(0.f, 0.f);
-  if (p.mode != 2) {
+  if (p.mode != 2 && p.mode != 6) {
     if (f_ok) {
       const float alpha = st->alpha, beta = st->beta;
       const int e0 = p.ant_ptr[ant], e1 = p.ant_ptr[ant + 1];
@@ -1108,10 +1139,12 @@ __global__ void __launch_bounds__(GK_THREADS) gains_kernel(const GainsParams p) 
       }
       return;
     }
-    if (!writer) return;
+    if (p.mode == 5 ? eg != 0 : !writer) return;  // LAMB pass 1 keeps warp 0 whole for the norm shuffles
   } else {
     if (eg != 0 || !f_ok) return;
-    if (p.peers.n > 1) {  // fused all-reduce: every rank's partial straight from its owner's memory, fixed order
+    if (p.mode == 6) {
+      // LAMB pass 2 needs no gradient
+    } else if (p.peers.n > 1) {  // fused all-reduce: every rank's partial straight from its owner's memory, fixed order
       const size_t ng = (size_t)p.nants * p.nfp;
       float2 tr[CALB2_MAX_RANKS], ti[CALB2_MAX_RANKS];
 #pragma unroll
@@ -1138,6 +1171,54 @@ __global__ void __launch_bounds__(GK_THREADS) gains_kernel(const GainsParams p) 
   }
   const float lr_t = st->lr_t;
   const float a_r[2] = {acc_r.x, acc_r.y}, a_i[2] = {acc_i.x, acc_i.y};
+  if (p.mode == 5) {  // LAMB pass 1 (warp 0): moments, then the CTA's share of ||theta||^2 and ||update||^2, fixed order
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};
+    if (f_ok) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const size_t oc = o + c;
+        float mr = p.m_r[oc], ur = p.u_r[oc], mi = p.m_i[oc], ui = p.u_i[oc];
+        const float tr = gr[oc], ti = gi[oc];
+        const float upr = lamb_moments(p.k, st, tr, a_r[c], mr, ur), upi = lamb_moments(p.k, st, ti, a_i[c], mi, ui);
+        p.m_r[oc] = mr;
+        p.u_r[oc] = ur;
+        p.m_i[oc] = mi;
+        p.u_i[oc] = ui;
+        if (f + c < p.nf) {
+          sums[0] += (double)tr * tr;
+          sums[1] += (double)upr * upr;
+          sums[2] += (double)ti * ti;
+          sums[3] += (double)upi * upi;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sums[q] += __shfl_down_sync(0xffffffffu, sums[q], off);
+    if (lane == 0) {
+      double* dst = p.lamb.gain_partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
+      for (int q = 0; q < 4; ++q) dst[q] = sums[q];
+    }
+    return;
+  }
+  if (p.mode == 6) {  // LAMB pass 2
+    const float rr = p.lamb.ratio[0], ri = p.lamb.ratio[1];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const size_t oc = o + c;
+      const float tr = gr[oc], ti = gi[oc];
+      const float nr = tr - rr * p.k.lr * lamb_update(p.k, st, tr, p.m_r[oc], p.u_r[oc]);
+      const float ni = ti - ri * p.k.lr * lamb_update(p.k, st, ti, p.m_i[oc], p.u_i[oc]);
+      p.g_r[src ^ 1][oc] = nr;
+      p.g_i[src ^ 1][oc] = ni;
+      if (st->snap && p.snap_r) {
+        p.snap_r[oc] = nr;
+        p.snap_i[oc] = ni;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const size_t oc = o + c;
@@ -1263,8 +1344,22 @@ struct CoeffParams {
                   // the streaming kernel's rows live in plane 0 only -- the other planes hold other layouts' data there
   int first_class_row;
   long long plane;  // floats per plane
-  int mode;       // 0: update; 1: gradient only; 3: snapshot copy only (freeze_model)
+  int mode;       // 0: update; 1: gradient only; 3: snapshot copy only (freeze_model);
+                  // 5: LAMB pass 1 (moments only); 6: LAMB pass 2 (apply with the variable's trust ratio)
+  const long long* var_bounds;  // [nvar + 1] coefficient ranges of the reference's per-chunk variables (LAMB)
+  int nvar;
+  const float* lamb_ratio;      // [2 + 2 nvar]
 };
+
+// the variable (chunk tensor of the reference's fg_r / fg_i lists) a coefficient belongs to
+__device__ __forceinline__ int lamb_var_of(const long long* bounds, int nvar, long long c) {
+  int lo = 0, hi = nvar - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (bounds[mid] <= c) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
 
 __global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
   const FitState* st = p.st;
@@ -1275,6 +1370,20 @@ __global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
     if (st->snap && p.snap_r) {
       p.snap_r[c] = p.c_r[c];
       p.snap_i[c] = p.c_i[c];
+    }
+    return;
+  }
+  if (p.mode == 6) {
+    const int v = lamb_var_of(p.var_bounds, p.nvar, c);
+    const float rr = p.lamb_ratio[2 + 2 * v], ri = p.lamb_ratio[3 + 2 * v];
+    const float tr = p.c_r[c], ti = p.c_i[c];
+    const float nr = tr - rr * p.k.lr * lamb_update(p.k, st, tr, p.m_r[c], p.u_r[c]);
+    const float ni = ti - ri * p.k.lr * lamb_update(p.k, st, ti, p.m_i[c], p.u_i[c]);
+    p.c_r[c] = nr;
+    p.c_i[c] = ni;
+    if (st->snap && p.snap_r) {
+      p.snap_r[c] = nr;
+      p.snap_i[c] = ni;
     }
     return;
   }
@@ -1325,6 +1434,15 @@ __global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
   }
   if (p.mode == 1) return;
   float mr = p.m_r[c], ur = p.u_r[c], mi = p.m_i[c], ui = p.u_i[c];
+  if (p.mode == 5) {
+    lamb_moments(p.k, st, p.c_r[c], gr, mr, ur);
+    lamb_moments(p.k, st, p.c_i[c], gi, mi, ui);
+    p.m_r[c] = mr;
+    p.u_r[c] = ur;
+    p.m_i[c] = mi;
+    p.u_i[c] = ui;
+    return;
+  }
   const float nr = opt_step<false, float>(p.k, st, p.c_r[c], gr, mr, ur, st->lr_t);
   const float ni = opt_step<false, float>(p.k, st, p.c_i[c], gi, mi, ui, st->lr_t);
   p.m_r[c] = mr;
@@ -1336,6 +1454,80 @@ __global__ void __launch_bounds__(256) coeffs_kernel(const CoeffParams p) {
   if (st->snap && p.snap_r) {
     p.snap_r[c] = nr;
     p.snap_i[c] = ni;
+  }
+}
+
+// LAMB norms of the coefficient variables: CTA (v, s) sums slice s of variable v's coefficients, update recomputed from the
+// moments pass 1 stored.  Thread-strided double sums, then a fixed-order tree: deterministic for a given launch shape.
+constexpr int LAMB_SPLIT = 16;
+struct LambNormParams {
+  const float* c_r;
+  const float* c_i;
+  const float* m_r;
+  const float* u_r;
+  const float* m_i;
+  const float* u_i;
+  const long long* var_bounds;
+  double* partials;  // [nvar][LAMB_SPLIT][4]
+  const FitState* st;
+  FitConsts k;
+};
+__global__ void __launch_bounds__(256) lamb_coef_norm_kernel(const LambNormParams p) {
+  __shared__ double red[8][4];
+  const FitState* st = p.st;
+  const int v = blockIdx.x, sp = blockIdx.y;
+  const long long c0 = p.var_bounds[v], c1 = p.var_bounds[v + 1];
+  const long long per = (c1 - c0 + LAMB_SPLIT - 1) / LAMB_SPLIT;
+  const long long a = c0 + sp * per, b = a + per < c1 ? a + per : c1;
+  double sums[4] = {0.0, 0.0, 0.0, 0.0};
+  if (st->upd_active)
+    for (long long c = a + threadIdx.x; c < b; c += 256) {
+      const float tr = p.c_r[c], ti = p.c_i[c];
+      const float ur = lamb_update(p.k, st, tr, p.m_r[c], p.u_r[c]), ui = lamb_update(p.k, st, ti, p.m_i[c], p.u_i[c]);
+      sums[0] += (double)tr * tr;
+      sums[1] += (double)ur * ur;
+      sums[2] += (double)ti * ti;
+      sums[3] += (double)ui * ui;
+    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sums[q] += __shfl_down_sync(0xffffffffu, sums[q], off);
+    if (lane == 0) red[warp][q] = sums[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    p.partials[((size_t)v * LAMB_SPLIT + sp) * 4 + threadIdx.x] = t;
+  }
+}
+
+// trust ratios (tfa LAMB: ||theta|| / ||update|| where both norms are positive, else 1), one warp per variable pair:
+// block 0 = the gain tables (g_r, g_i), block 1 + v = coefficient variable v (fg_r[v], fg_i[v])
+struct LambRatioParams {
+  const double* gain_partials;
+  int n_gain_partials;
+  const double* coef_partials;
+  float* ratio;
+};
+__global__ void __launch_bounds__(32) lamb_ratio_kernel(const LambRatioParams p) {
+  const int lane = threadIdx.x;
+  const double* src = blockIdx.x == 0 ? p.gain_partials : p.coef_partials + (size_t)(blockIdx.x - 1) * LAMB_SPLIT * 4;
+  const int n = blockIdx.x == 0 ? p.n_gain_partials : LAMB_SPLIT;
+  double sums[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = lane; i < n; i += 32)
+    for (int q = 0; q < 4; ++q) sums[q] += src[(size_t)i * 4 + q];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sums[q] += __shfl_down_sync(0xffffffffu, sums[q], off);
+  if (lane == 0) {
+    for (int h = 0; h < 2; ++h) {
+      const float wn = (float)sqrt(sums[2 * h]), un = (float)sqrt(sums[2 * h + 1]);
+      p.ratio[2 * blockIdx.x + h] = (wn > 0.f && un > 0.f) ? wn / un : 1.f;
+    }
   }
 }
 

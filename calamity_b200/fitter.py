@@ -5,7 +5,8 @@ import numpy as np
 
 from . import _native as nat
 
-OPTIMIZER_IDS = {"Adamax": 0, "Adam": 1, "SGD": 2, "RMSprop": 3, "Adagrad": 4, "Adadelta": 5, "Nadam": 6, "Ftrl": 7}
+OPTIMIZER_IDS = {"Adamax": 0, "Adam": 1, "SGD": 2, "RMSprop": 3, "Adagrad": 4, "Adadelta": 5, "Nadam": 6, "Ftrl": 7,
+                 "LAMB": 8}
 # tf.keras.optimizers defaults (TensorFlow >= 2.4 OptimizerV2), used when **opt_kwargs omits a field
 KERAS_DEFAULTS = {
     "Adamax": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
@@ -17,9 +18,11 @@ KERAS_DEFAULTS = {
     "Nadam": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
     "Ftrl": dict(learning_rate=0.001, learning_rate_power=-0.5, initial_accumulator_value=0.1,
                  l1_regularization_strength=0.0, l2_regularization_strength=0.0),
+    # tensorflow_addons.optimizers.LAMB (calibration.py:15, 26)
+    "LAMB": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-6, weight_decay=0.0),
 }
-# names the reference's OPTIMIZERS dict accepts (calibration.py:17-27); those without a device
-# implementation raise NotImplementedError instead of silently substituting something else
+# names the reference's OPTIMIZERS dict accepts (calibration.py:17-27); all have a device implementation (LAMB: float32
+# plans on one GPU; anything else raises the library's "unsupported" error, nothing is substituted)
 REFERENCE_OPTIMIZERS = ("Adadelta", "Adam", "Adamax", "Ftrl", "Nadam", "SGD", "RMSprop", "Adagrad", "LAMB")
 
 
@@ -138,7 +141,13 @@ class FitPlan:
             l1_regularization_strength=hp.get("l1_regularization_strength", 0.0),
             l2_regularization_strength=hp.get("l2_regularization_strength", 0.0),
             learning_rate_power=hp.get("learning_rate_power", 0.0), nesterov=int(bool(hp.get("nesterov", False))),
+            weight_decay=hp.get("weight_decay", 0.0),
         )
+        if optimizer == "LAMB":
+            # the trust ratio is per tf.Variable: the reference keeps one coefficient variable per chunk (calibration.py:560-567)
+            bounds = np.ascontiguousarray(self.layout.chunk_coef_bounds(), dtype=np.int64)
+            nat.check(self._lib.calb2_plan_set_variables(self._handle, len(bounds) - 1,
+                                                         bounds.ctypes.data_as(C.POINTER(C.c_int64))))
         hist = np.zeros(max(1, int(maxsteps)), dtype=self.dtype)
         res = nat.FitResult()
         nat.check(self._lib.calb2_fit(self._handle, C.byref(opts), self._ptr(hist), C.byref(res)))

@@ -120,6 +120,16 @@ class RaggedLayout:
             b += n
         return out
 
+    def chunk_coef_bounds(self):
+        """[nchunks + 1] coefficient offsets of the chunks: chunk c is the reference's variable pair fg_r[c] / fg_i[c]
+        (calibration.py:560-567).  Chunks without stored coefficients are skipped."""
+        b = [0]
+        for ch in self.chunks:
+            e = int(self.group_coef0[ch["group0"] + ch["ngrps"]])
+            if e > b[-1]:
+                b.append(e)
+        return np.asarray(b, dtype=np.int64)
+
     def flatten_coeffs(self, chunk_coeffs):
         """list of [nvecs, ngrps, 1, 1] -> [ncoef] (layout dtype)."""
         flat = np.zeros(self.ncoef, dtype=self.dtype)

@@ -49,10 +49,11 @@ enum {
   CALB2_ERR_TIMEOUT = -7   /* peer exchange: a rank did not publish its partial sums in time (fit aborted on every rank) */
 };
 
-/* tf.optimizers.* of calibration.py:17-27 that have a device implementation (all but tensorflow-addons' LAMB). */
+/* The OPTIMIZERS table of calibration.py:17-27: the eight tf.optimizers.* and tensorflow-addons' LAMB (calibration.py:15, 26;
+ * float32 plans on one GPU; its trust ratio is per VARIABLE, see calb2_plan_set_variables). */
 enum {
   CALB2_OPT_ADAMAX = 0, CALB2_OPT_ADAM = 1, CALB2_OPT_SGD = 2, CALB2_OPT_RMSPROP = 3, CALB2_OPT_ADAGRAD = 4,
-  CALB2_OPT_ADADELTA = 5, CALB2_OPT_NADAM = 6, CALB2_OPT_FTRL = 7
+  CALB2_OPT_ADADELTA = 5, CALB2_OPT_NADAM = 6, CALB2_OPT_FTRL = 7, CALB2_OPT_LAMB = 8
 };
 
 /* dtype of calibrate_and_model_tensor (calibration.py:974): element type of a plan's floating point buffers. */
@@ -114,6 +115,7 @@ typedef struct {
   double l2_regularization_strength;  /* Ftrl */
   double learning_rate_power;         /* Ftrl */
   int32_t nesterov;                   /* SGD */
+  double weight_decay;                /* LAMB (tfa name: weight_decay / weight_decay_rate) */
 } calb2_fit_options;
 
 typedef struct {
@@ -173,6 +175,12 @@ int calb2_plan_get_info(const calb2_plan* plan, calb2_plan_info* info);
  * group's [nslots][ncomp][nfreqs] block (plan dtype) (row k of slot s = fg_model_comps[c][k, g, b, :] for any
  * baseline b of slot s, calibration.py:178-183).  Equal pointers are uploaded once. */
 int calb2_plan_set_basis(calb2_plan* plan, int32_t group_first, int32_t ngroups, const void* const* blocks);
+
+/* The reference keeps the foreground coefficients as one tf.Variable PER CHUNK (fg_r[c], fg_i[c], calibration.py:560-567);
+ * optimizers whose rule couples the elements of a variable (LAMB's layer-wise trust ratio) need to know the chunks:
+ * coef_bounds[0] = 0 < ... < coef_bounds[nvars] = n_c_nz, variable v = coefficients [coef_bounds[v], coef_bounds[v+1]).
+ * Never called = one variable holding every coefficient.  The gain tables g_r and g_i are one variable each. */
+int calb2_plan_set_variables(calb2_plan* plan, int32_t nvars, const int64_t* coef_bounds);
 
 /* Per integration: mirrors tensorize_data's outputs (calibration.py:1184-1194), [nbls_total][nfreqs]. */
 int calb2_set_integration(calb2_plan* plan, const void* data_r, const void* data_i, const void* wgts);

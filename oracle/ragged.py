@@ -106,10 +106,15 @@ class RaggedProblem:
 
     def fit(self, g_r, g_i, c_r, c_i, data_r, data_i, wgts, use_min=False, tol=1e-14, maxsteps=10000,
             optimizer="Adamax", freeze_model=False, n_profile_steps=0, model_regularization=None,
-            prior_r_sum=None, prior_i_sum=None, **opt_kwargs):
+            prior_r_sum=None, prior_i_sum=None, coef_var_bounds=None, **opt_kwargs):
         """Loop of restatement.fit (calibration.py:447-738) on flat parameters.  The Keras rules are elementwise,
-        so applying them to the flat coefficient vector equals applying them to the per-chunk tensors."""
+        so applying them to the flat coefficient vector equals applying them to the per-chunk tensors; LAMB's trust
+        ratio is per variable, so for it `coef_var_bounds` ([nchunks + 1] coefficient offsets) splits the flat vectors
+        into the reference's per-chunk variables fg_r[c] / fg_i[c] (calibration.py:560-567), in the reference's order
+        g_r, g_i, fg_r[0..], fg_i[0..]."""
         opt = R.KerasOptimizer(optimizer, **opt_kwargs)
+        vb = [0, None] if coef_var_bounds is None else [int(b) for b in coef_var_bounds]
+        nv = len(vb) - 1
         dt = self.dtype
         g_r, g_i, c_r, c_i = (np.array(x, dtype=dt) for x in (g_r, g_i, c_r, c_i))
         data_r, data_i, wgts = (np.asarray(x, dtype=dt) for x in (data_r, data_i, wgts))
@@ -121,7 +126,9 @@ class RaggedProblem:
             if freeze_model:
                 opt.apply([g_r, g_i], [dgr, dgi], [True, True])
             else:
-                opt.apply([g_r, g_i, c_r, c_i], [dgr, dgi, dcr, dci], [True, True, False, False])
+                opt.apply([g_r, g_i] + [c_r[vb[v] : vb[v + 1]] for v in range(nv)] + [c_i[vb[v] : vb[v + 1]] for v in range(nv)],
+                          [dgr, dgi] + [dcr[vb[v] : vb[v + 1]] for v in range(nv)] + [dci[vb[v] : vb[v + 1]] for v in range(nv)],
+                          [True, True] + [False] * (2 * nv))
             return loss
 
         for _ in range(n_profile_steps):

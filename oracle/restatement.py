@@ -254,6 +254,8 @@ KERAS_DEFAULTS = {
     "Nadam": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7),
     "Ftrl": dict(learning_rate=0.001, learning_rate_power=-0.5, initial_accumulator_value=0.1,
                  l1_regularization_strength=0.0, l2_regularization_strength=0.0),
+    # tensorflow_addons.optimizers.LAMB (calibration.py:15, 26); exclude_from_* lists are not restated
+    "LAMB": dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-6, weight_decay=0.0),
 }
 
 
@@ -350,6 +352,22 @@ class KerasOptimizer:
                 else:  # ApplyKerasMomentum
                     m[...] = m * mom - lr0 * g
                     p += (m * mom - lr0 * g) if self.hp["nesterov"] else m
+                continue
+            if self.name == "LAMB":
+                # tfa.optimizers.LAMB._resource_apply_dense (the _sparse variant computes the same expressions): Adam moments
+                # with bias correction, then a PER-VARIABLE trust ratio ||w|| / ||update|| (1 when either norm is 0)
+                lr, b1, b2, eps, wd = (dt(self.hp[k]) for k in ("learning_rate", "beta_1", "beta_2", "epsilon", "weight_decay"))
+                m[...] = m * b1 + g * (dt(1) - b1)
+                u[...] = u * b2 + (g * g) * (dt(1) - b2)
+                m_hat = m / (dt(1) - dt(np.power(b1, dt(t))))
+                u_hat = u / (dt(1) - dt(np.power(b2, dt(t))))
+                upd = m_hat / (np.sqrt(u_hat) + eps)
+                if wd != 0:
+                    upd = upd + wd * p
+                w_norm = dt(np.sqrt(np.sum(np.square(p, dtype=np.float64))))
+                g_norm = dt(np.sqrt(np.sum(np.square(upd, dtype=np.float64))))
+                ratio = (w_norm / g_norm) if (w_norm > 0 and g_norm > 0) else dt(1)
+                p -= ratio * lr * upd
                 continue
             if self.name not in ("Adamax", "Adam"):
                 self._other_rules(p, g, m, u, t, dt, nadam)

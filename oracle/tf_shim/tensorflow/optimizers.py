@@ -157,3 +157,25 @@ class Ftrl(_Base):
         v._t.copy_(torch.where(lin.abs() > l1, (torch.sign(lin) * l1 - lin) / quadratic, torch.zeros_like(lin)))
 
 
+
+
+class LAMB(_Base):
+    """tensorflow_addons.optimizers.LAMB (_resource_apply_dense / _sparse compute the same expressions): Adam moments with bias
+    correction and a per-variable trust ratio ||w|| / ||update||."""
+
+    defaults = dict(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-6, weight_decay=0.0)
+
+    def _update(self, v, g, sparse):
+        dt = v._t.dtype
+        lr, b1, b2, eps, wd = (torch.tensor(self.hp[k], dtype=dt) for k in ("learning_rate", "beta_1", "beta_2", "epsilon", "weight_decay"))
+        one = torch.tensor(1.0, dtype=dt)
+        t = torch.tensor(float(self.iterations), dtype=dt)
+        m, u = self.slots.setdefault(id(v), (torch.zeros_like(v._t), torch.zeros_like(v._t)))
+        m.copy_(m * b1 + g * (one - b1))
+        u.copy_(u * b2 + (g * g) * (one - b2))
+        upd = (m / (one - torch.pow(b1, t))) / (torch.sqrt(u / (one - torch.pow(b2, t))) + eps)
+        if float(wd) != 0.0:
+            upd = upd + wd * v._t
+        w_norm, g_norm = torch.linalg.vector_norm(v._t), torch.linalg.vector_norm(upd)
+        ratio = (w_norm / g_norm) if (float(w_norm) > 0 and float(g_norm) > 0) else one
+        v._t -= ratio * lr * upd

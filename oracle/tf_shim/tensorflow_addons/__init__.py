@@ -1,7 +1,10 @@
+"""tensorflow_addons stand-in for oracle/tf_shim: only `optimizers.LAMB`, the one symbol the reference touches
+(calibration.py:15, 26).  The rule is oracle/tf_shim/tensorflow/optimizers.py:LAMB (tfa LAMB._resource_apply_dense)."""
+from tensorflow.optimizers import LAMB as _LAMB
+
+
 class _Optimizers:
-    class LAMB:
-        def __init__(self, **kwargs):
-            raise NotImplementedError("LAMB is not restated in tf_shim")
+    LAMB = _LAMB
 
 
 optimizers = _Optimizers()

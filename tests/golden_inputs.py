@@ -39,6 +39,8 @@ FIT_CASES = {
     "adagrad_sum": dict(optimizer="Adagrad", maxsteps=30, tol=0.0, learning_rate=1e-2, model_regularization="sum"),
     "adadelta": dict(optimizer="Adadelta", maxsteps=30, tol=0.0, learning_rate=1.0),
     "nadam": dict(optimizer="Nadam", maxsteps=30, tol=0.0, learning_rate=1e-2),
+    # tensorflow_addons' LAMB (calibration.py:15, 26): the reference's loop, the shim's statement of the tfa rule
+    "lamb": dict(optimizer="LAMB", maxsteps=30, tol=0.0, learning_rate=1e-2, weight_decay=1e-2),
 }
 
 

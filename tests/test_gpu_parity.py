@@ -88,13 +88,15 @@ OTHER_OPTIMIZERS = [
     ("Nadam", dict(learning_rate=1e-2)),
     ("Ftrl", dict(learning_rate=1e-2)),
     ("Ftrl", dict(learning_rate=1e-2, l1_regularization_strength=1e-6, l2_regularization_strength=1e-4)),
+    ("LAMB", dict(learning_rate=1e-2)),
+    ("LAMB", dict(learning_rate=1e-2, weight_decay=1e-2)),
 ]
 
 
 @pytest.mark.parametrize("optimizer,opt_kw", OTHER_OPTIMIZERS)
 def test_other_keras_optimizers(native_built, optimizer, opt_kw):
-    """The remaining entries of the reference's OPTIMIZERS table (calibration.py:17-27, all but LAMB): device
-    trajectories against the float64 restatement of the Keras rules, same tolerances as Adamax / Adam."""
+    """The remaining entries of the reference's OPTIMIZERS table (calibration.py:17-27, tensorflow-addons' LAMB included):
+    device trajectories against the float64 restatement of the Keras rules, same tolerances as Adamax / Adam."""
     nsteps = 40
     prob = small_problem("test6", init_gain_scatter=0.02, coeff_error=0.05)
     t64 = reference_tensors(prob, np.float64)
@@ -130,13 +132,67 @@ def test_other_keras_optimizers(native_built, optimizer, opt_kw):
         assert rel_err(ours, ref64) < max(1e-4, 3.0 * rel_err(ref32, ref64)), (rel_err(ours, ref64), rel_err(ref32, ref64))
 
 
-def test_lamb_is_refused_and_unknown_names_raise_keyerror(native_built):
+def test_unknown_optimizer_names_raise_keyerror(native_built):
     prob = small_problem("test6")
     plan = _plan(prob)
-    with pytest.raises(NotImplementedError):
-        plan.fit(optimizer="LAMB", maxsteps=1)
     with pytest.raises(KeyError):  # calibration.py:571, OPTIMIZERS[optimizer]
         plan.fit(optimizer="NotAnOptimizer", maxsteps=1)
+    plan.close()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(use_min=True, weight_decay=1e-2), dict(model_regularization="sum"),
+                                dict(freeze_model=True)])
+def test_lamb_trust_ratio_is_per_chunk_variable(native_built, kw):
+    """LAMB (calibration.py:15, 26) scales every tf.Variable's step by its own ||w|| / ||update||.  The reference holds one
+    coefficient variable per chunk (calibration.py:560-567): a problem with several chunks (joint groups next to DPSS
+    groups of different sizes) must follow the float64 restatement run on the same per-chunk variables -- and must NOT
+    follow the one that treats all coefficients as a single variable."""
+    from calamity_b200.fitter import FitPlan
+    from helpers import mixed_problem
+    from oracle.ragged import RaggedProblem
+
+    p = mixed_problem(nants=24, nfreqs=96, seed=3, n_dpss_bls=120, joint=((3, 9, 20), (2, 7, 12)))
+    bounds = p.lay.chunk_coef_bounds()
+    assert len(bounds) - 1 >= 3, bounds
+    nsteps = 30
+    fit_kw = dict(optimizer="LAMB", maxsteps=nsteps, tol=0.0, learning_rate=1e-2, **kw)
+    if kw.get("model_regularization") == "sum":
+        fit_kw.update(prior_r_sum=0.9 * float(np.sum(p.data_r * p.wgts)), prior_i_sum=1.1 * float(np.sum(p.data_i * p.wgts)))
+    rp = RaggedProblem(p.lay, dtype=np.float64)
+    args = [np.asarray(x, dtype=np.float64) for x in (p.g0_r, p.g0_i, p.c0_r, p.c0_i, p.data_r, p.data_i, p.wgts)]
+    o = rp.fit(*args, coef_var_bounds=bounds, **fit_kw)
+    o_one = rp.fit(*args, **fit_kw)
+    plan = FitPlan(p.lay, device=0)
+    plan.set_integration(p.data_r, p.data_i, p.wgts)
+    plan.set_gains(p.g0_r, p.g0_i)
+    plan.set_coeffs(p.c0_r, p.c0_i)
+    hist, res = plan.fit(**fit_kw)
+    g_r, g_i = plan.get_gains()
+    c_r, c_i = plan.get_coeffs()
+    plan.close()
+    ref = np.asarray(o[4]["loss"], dtype=np.float64)
+    err = np.abs(hist.astype(np.float64) - ref) / ref
+    one = np.abs(np.asarray(o_one[4]["loss"], dtype=np.float64) - ref) / ref
+    print(f"\nLAMB {kw}: {len(bounds) - 1} variables, max rel loss err {err.max():.2e} (single-variable restatement is {one.max():.2e} away)")
+    assert res["nsteps_recorded"] == nsteps
+    assert err.max() < 1e-5, err.max()
+    if not kw.get("freeze_model"):
+        assert one.max() > 100 * err.max(), (one.max(), err.max())  # the test can tell the two readings apart
+    for ours, ref64 in ((g_r, o[0]), (g_i, o[1]), (c_r, o[2]), (c_i, o[3])):
+        assert rel_err(ours, ref64) < 1e-4, rel_err(ours, ref64)
+
+
+def test_lamb_needs_a_float32_plan(native_built):
+    from calamity_b200 import _native as nat
+    from calamity_b200.fitter import FitPlan
+
+    prob = small_problem("test6")
+    plan = FitPlan(prob.layout(np.float64), device=0)
+    plan.set_integration(prob.data_r, prob.data_i, prob.wgts)
+    plan.set_gains(prob.g0_r, prob.g0_i)
+    plan.set_coeffs(prob.c0_r, prob.c0_i)
+    with pytest.raises(nat.NativeError, match=r"\(-3\).*float32"):  # CALB2_ERR_UNSUPPORTED
+        plan.fit(optimizer="LAMB", maxsteps=1)
     plan.close()
 
 
