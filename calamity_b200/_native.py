@@ -113,6 +113,7 @@ _SIGNATURES = {
     "calb2_plan_destroy": (C.c_int, [C.c_void_p]),
     "calb2_plan_get_info": (C.c_int, [C.c_void_p, C.POINTER(PlanInfo)]),
     "calb2_plan_set_basis": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "calb2_debug_tc_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "calb2_plan_set_variables": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "calb2_set_integration": (C.c_int, [C.c_void_p, _FP, _FP, _FP]),
     "calb2_set_gains": (C.c_int, [C.c_void_p, _FP, _FP]),

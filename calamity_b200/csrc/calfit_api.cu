@@ -187,11 +187,14 @@ struct calb2_plan {
   DevBuf<MTileDesc> d_mtiles[2][2];
   // tensor-core shape: its CTAs (64 groups of a class of <= 128 vectors) and, when it is in use, the 256-thread CTAs of the
   // remaining small classes (129-160 vectors)
-  std::vector<MTileDesc> mt_tc, mt_small_rest;
-  DevBuf<MTileDesc> d_mt_tc, d_mt_small_rest;
+  std::vector<MTileDesc> mt_tc, mt_small_rest, mt_large_rest;  // tensor-core tiles; the classes it does not take, per CUDA-core shape
+  DevBuf<MTileDesc> d_mt_tc, d_mt_small_rest, d_mt_large_rest;
   DevBuf<float> At;
   bool tc_enabled = false;
+  size_t tc_smem_bytes = 0;           // dynamic shared memory of the tensor-core launch: the largest class's layout
   unsigned int* tc_dbg = nullptr;     // mapped host memory: record of a tensor-core wait that timed out
+  DevBuf<long long> tc_prof;          // CALB2_TC_PROF=<cta>: clock stamps of one CTA of the tensor-core kernel
+  int tc_prof_cta = -1;
   int nseg[2] = {1, 1};               // channel segments per class tile = planes of dcpart in use
   long long dc_plane = 0;             // floats per plane of dcpart
   int first_class_row = 0;            // rows below it belong to the streaming path (plane 0 only)
@@ -396,7 +399,8 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
   const int n_tc = use_tc ? (int)pl->mt_tc.size() : 0;
   const MTileDesc* small_tiles = use_tc ? pl->d_mt_small_rest.p : pl->d_mtiles[v][0].p;
   const int n_small = use_tc ? (int)pl->mt_small_rest.size() : (int)pl->mtiles[v][0].size();
-  const int n_large = (int)pl->mtiles[v][1].size();
+  const MTileDesc* large_tiles = use_tc ? pl->d_mt_large_rest.p : pl->d_mtiles[v][1].p;
+  const int n_large = use_tc ? (int)pl->mt_large_rest.size() : (int)pl->mtiles[v][1].size();
   SharedParams sp{};
   if (n_small + n_large > 0) {
     sp.A = hp.A;
@@ -433,7 +437,7 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
       if (e != cudaSuccess) return e;
       sl = pl->stream2;
     }
-    sp.tiles = pl->d_mtiles[v][1].p;
+    sp.tiles = large_tiles;
     sp.partials = hp.partials + (size_t)(nitems + n_small) * 4;
     cudaError_t e = launch_shared_shape(sum, pl->cls_single_bl, 1, sp, n_large, sl);
     if (e == cudaSuccess && fork_large) e = cudaEventRecord(pl->ev_join, pl->stream2);
@@ -472,14 +476,16 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
     tp.st = hp.st;
     tp.nfp = hp.nfp;
     tp.dbg = pl->tc_dbg;
+    tp.prof = pl->tc_prof.p;
+    tp.prof_cta = pl->tc_prof_cta;
     static bool configured[MAX_DEVICES] = {};
     const int dev = current_device();
     if (!configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(shared_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg::SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(shared_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return e;
       configured[dev] = true;
     }
-    shared_tc_kernel<<<n_tc, TcCfg::NTHR, TcCfg::SMEM_BYTES, s>>>(tp);
+    shared_tc_kernel<<<n_tc, TcCfg::NTHR, pl->tc_smem_bytes, s>>>(tp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -496,13 +502,13 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
 static int n_partials(const calb2_plan* pl, bool sum) {
   const int v = sum ? 1 : 0;
   if (pl->tc_enabled && !sum && !pl->mt_tc.empty())
-    return (int)(pl->items.size() + pl->mt_small_rest.size() + pl->mtiles[0][1].size() + pl->mt_tc.size());
+    return (int)(pl->items.size() + pl->mt_small_rest.size() + pl->mt_large_rest.size() + pl->mt_tc.size());
   return (int)(pl->items.size() + pl->mtiles[v][0].size() + pl->mtiles[v][1].size());
 }
 static int n_partials_max(const calb2_plan* pl) {
   int n = 0;
   for (int v = 0; v < 2; ++v) n = std::max(n, (int)(pl->items.size() + pl->mtiles[v][0].size() + pl->mtiles[v][1].size()));
-  return std::max(n, (int)(pl->items.size() + pl->mt_small_rest.size() + pl->mtiles[0][1].size() + pl->mt_tc.size()));
+  return std::max(n, (int)(pl->items.size() + pl->mt_small_rest.size() + pl->mt_large_rest.size() + pl->mt_tc.size()));
 }
 
 static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, int store_v, int init_mode) {
@@ -1071,6 +1077,16 @@ int calb2_debug_tc_record(uint32_t* out16) {
   return 0;
 }
 
+int calb2_debug_tc_profile(calb2_plan* pl, int64_t* out, int32_t n) {
+  if (!pl || !out) return fail(CALB2_ERR_ARG, "null argument");
+  if (!pl->tc_prof.p) return fail(CALB2_ERR_STATE, "set CALB2_TC_PROF=<cta> before creating the plan");
+  CU(cudaSetDevice(pl->device));
+  CU(cudaStreamSynchronize(pl->stream));
+  const size_t m = std::min<size_t>((size_t)std::max(n, 0), pl->tc_prof.n);
+  CU(cudaMemcpy(out, pl->tc_prof.p, m * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int calb2_device_count(int32_t* count) {
   if (!count) return fail(CALB2_ERR_ARG, "null argument");
   int n = 0;
@@ -1329,12 +1345,17 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   {
     // tensor-core shape: on by default for single-baseline slots; CALB2_TC=0 keeps every class on the CUDA-core shapes
     pl->tc_enabled = pl->cls_single_bl && !(getenv("CALB2_TC") && atoi(getenv("CALB2_TC")) == 0);
+    // a tensor-core CTA costs the same for 1 or 64 groups (128 accumulator rows): classes with fewer than tc_min members stay
+    // on the CUDA-core shapes (32 / 64 groups per CTA, cost by 8-group block)
+    int tc_min = 16;
+    if (getenv("CALB2_TC_MIN")) tc_min = std::max(1, atoi(getenv("CALB2_TC_MIN")));
     long long tc_off = 0;
     for (auto& ci : pl->classes) {
-      if (!pl->tc_enabled) ci.tc = false;
+      if (!pl->tc_enabled || ci.nmembers < tc_min) ci.tc = false;
       if (ci.tc) {
         ci.tc_off = tc_off;
         tc_off += (long long)pl->ntiles_c * 4 * ci.kpt * SHARED_FT;
+        pl->tc_smem_bytes = std::max(pl->tc_smem_bytes, (size_t)tc_layout(ci.kpt).total);
       }
     }
   }
@@ -1367,7 +1388,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
             mt.j1 = (int)((long long)pl->ntiles_c * (sg + 1) / nseg);
             mt.seg = sg;
             pl->mtiles[v][shape].push_back(mt);
-            if (v == 0 && shape == 0 && !ci.tc) pl->mt_small_rest.push_back(mt);
+            if (v == 0 && !ci.tc) (shape == 0 ? pl->mt_small_rest : pl->mt_large_rest).push_back(mt);
           }
         if (v == 0 && ci.tc)  // the same class as 64-group tiles of the tensor-core shape
           for (int m0 = 0; m0 < ci.nmembers; m0 += TcCfg::MS)
@@ -1393,6 +1414,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
       for (int shape = 0; shape < 2; ++shape) std::stable_sort(pl->mtiles[v][shape].begin(), pl->mtiles[v][shape].end(), by_cost);
       if (v == 0) {
         std::stable_sort(pl->mt_small_rest.begin(), pl->mt_small_rest.end(), by_cost);
+        std::stable_sort(pl->mt_large_rest.begin(), pl->mt_large_rest.end(), by_cost);
         std::stable_sort(pl->mt_tc.begin(), pl->mt_tc.end(), by_cost);
       }
     }
@@ -1537,6 +1559,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(dalloc(pl->partials, (size_t)n_partials_max(pl) * 4, pl));
   TRY(upload(pl->d_mt_tc, pl->mt_tc, pl));
   TRY(upload(pl->d_mt_small_rest, pl->mt_small_rest, pl));
+  TRY(upload(pl->d_mt_large_rest, pl->mt_large_rest, pl));
   {
     long long tc_floats = 0;
     for (const auto& ci : pl->classes)
@@ -1562,6 +1585,10 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     else {
       memset(pl->tc_dbg, 0, 64);
       g_tc_dbg = pl->tc_dbg;
+    }
+    if (const char* e = getenv("CALB2_TC_PROF")) {
+      pl->tc_prof_cta = atoi(e);
+      if (!rc) rc = dalloc(pl->tc_prof, (size_t)TC_PROF_SLOTS * TC_PROF_TILES, pl);
     }
   }
   if (rc) {
@@ -1600,6 +1627,7 @@ int calb2_plan_destroy(calb2_plan* pl) {
     for (int shape = 0; shape < 2; ++shape) pl->d_mtiles[v][shape].release();
   pl->d_mt_tc.release();
   pl->d_mt_small_rest.release();
+  pl->d_mt_large_rest.release();
   pl->At.release();
   pl->d_cslots.release();
   pl->d_cs_slot.release();

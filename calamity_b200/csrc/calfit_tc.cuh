@@ -1,4 +1,4 @@
-// Tensor-core shape of the shared-basis pass (sm_100a: tcgen05 + TMEM), for basis classes of <= 128 vectors, plain chi^2,
+// Tensor-core shape of the shared-basis pass (sm_100a: tcgen05 + TMEM), for basis classes of <= 208 vectors, plain chi^2,
 // single-baseline slots.  Same work item as calfit_shared.cuh -- 64 groups of ONE class through a range of 32-channel tiles --
 // with both contractions on the 5th-generation tensor cores as TF32 MMAs with a 3-term split (hi.hi + hi.lo + lo.hi; plain TF32
 // would break the 1e-5 loss tolerance):
@@ -15,15 +15,23 @@
 //                                                             all tiles of the CTA
 //
 // The tensor core accumulates in float32 with truncation (measured: tools/tc_probe.cu, profiles/round2_tcgen05_probe.log: 26
-// chained accumulations cost 6e-7 relative).  V therefore goes to TWO partial accumulators (half of the k-steps each) plus one
-// for the two small split terms, and the three are added in registers with round-to-nearest.
+// chained accumulations cost 6e-7 relative).  Where TMEM has the room, V goes to TWO partial accumulators (half of the k-steps
+// each) plus one for the two small split terms, and the three are added in registers with round-to-nearest.
 //
-// One warp issues the MMAs and the bulk copies (one thread), eight warps do phase Q; mbarriers connect them:
-//   full[s]  tile landed (TMA)            -> MMA warp          free[s]  phase B of the tile in stage s retired (tcgen05.commit) -> MMA warp refills s
-//   v[b]     phase F retired (commit)     -> phase-Q warps     bar_q    phase Q done (256 arrivals)                             -> MMA warp issues B
-// Issue order of the MMA thread: F(0); then per tile j: F(j + 1) | wait Q(j) | B(j) | refill -- the tensor pipe executes in
-// issue order, so B(j) reads dL/dv(j) out of V buffer j & 1 before F(j + 2) overwrites it.
-// Descriptor encodings follow cute/arch/mma_sm100_desc.hpp; every operand form used here is checked by tools/tc_probe.cu.
+// TMEM (512 columns) and shared memory (227 KB) set three modes by the class's padded vector count kpt (tc_layout):
+//   kpt <= 128   C hi | dC | 2 V buffers x (2 partials + small) | 2 dL/dv-lo     2 + 2 tile stages     F(j+1) overlaps Q(j)
+//   kpt <= 160   C hi | dC | 2 V buffers x (1 partial  + small) | 2 dL/dv-lo     2 + 1 tile stages     F(j+1) overlaps Q(j)
+//   kpt <= 208   C hi | dC | 1 V buffer  x (1 partial  + small) | 1 dL/dv-lo     1 + 1 tile stages     F, Q, B in turn
+// (the MN-major pair of a tile -- phase F's operand -- and its K-major pair -- phase B's -- are separate rings: the first is
+// free again once phase F retired, the second only after phase B; one copy cannot serve both, the K-major descriptor does not
+// take the 32-byte-base swizzle: tools/tc_probe.cu T8).
+//
+// One warp issues the MMAs and the bulk copies (one elected lane), eight warps do phase Q; mbarriers connect them:
+//   full_f[s] / full_b[s]  tile pair landed (TMA) -> MMA warp      free[s]  phase B retired (tcgen05.commit) -> K-major refill;  done -> epilogue
+//   v[b]     phase F retired (commit)     -> phase-Q warps, MN-major refill      q[b]  phase Q done (256 arrivals) -> MMA warp issues B
+// The tensor pipe executes in issue order, so B(j) reads dL/dv(j) out of its V buffer before the next phase F into that buffer
+// overwrites it.  Descriptor encodings follow cute/arch/mma_sm100_desc.hpp; every operand form used here is checked by
+// tools/tc_probe.cu.
 #pragma once
 #include "calfit_shared.cuh"
 
@@ -31,32 +39,42 @@ namespace calb2 {
 
 struct TcCfg {
   static constexpr int MS = 64, FT = 32;
-  static constexpr int KPMAX = 128;                          // rows per class tile (ncomp rounded up to 16)
+  static constexpr int KPMAX = 208;                          // rows per class tile (ncomp rounded up to 16)
   static constexpr int NEPI = 256;                           // 8 phase-Q warps: TMEM lane quadrant = warp & 3, column half = warp >> 2
   static constexpr int NTHR = NEPI + 32;                     // + the MMA / TMA warp
-  static constexpr int STAGE_BYTES = 4 * KPMAX * 128;        // [b32 hi | b32 lo | std hi | std lo], 64 KB; the two halves are
-                                                             // separate rings: the MN-major pair is free again once phase F
-                                                             // retired, the K-major pair only after phase B
-  static constexpr int OFF_STAGE = 0;
-  static constexpr int OFF_CLO = 2 * STAGE_BYTES;            // C lo: [kp / 32 chunks][128 rows][128 B], K-major SWIZZLE_128B
-  static constexpr int OFF_CS = OFF_CLO + (KPMAX / 32) * 128 * 128;
-  static constexpr int OFF_ANT = OFF_CS + MS * 16;
-  static constexpr int OFF_RED = OFF_ANT + MS * 8;
-  static constexpr int OFF_BAR = OFF_RED + 8 * 16;           // full_f[2], full_b[2], free[2], v[2], q[2]
-  static constexpr int OFF_TMEM = OFF_BAR + 10 * 8;
-  static constexpr int SMEM_BYTES = OFF_TMEM + 16;
-  // TMEM columns (512 allocated)
-  static constexpr int COL_CHI = 0;     // C hi, 128
-  static constexpr int COL_DC = 128;    // dC accumulator, 128
-  // two V buffers (tile parity) so that phase F of tile j + 1 runs on the tensor cores while phase Q of tile j runs on the CUDA
-  // cores: [partial 0 | partial 1 | small split terms], 32 columns each; dL/dv hi is written over partial 0 of its own buffer
-  static constexpr int COL_V = 256;
-  static constexpr int V_STRIDE = 96;
-  static constexpr int V_SMALL = 64;    // offset of the small-term accumulator inside a V buffer
-  static constexpr int COL_QLO = 448;   // dL/dv lo, two buffers of 32
-  static constexpr int NPART = 2;
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static constexpr int NPART_MAX = 2;
 };
+
+// TMEM columns and shared-memory offsets of a CTA whose class has kpt (multiple of 16) padded vectors
+struct TcLayout {
+  int nbuf, npart, n_mn, n_k;
+  int col_dc, col_v, v_stride, v_small, col_qlo;
+  uint32_t sub_bytes, half_bytes;   // one of the four copies of a tile; the MN-major pair / the K-major pair
+  uint32_t off_k, off_clo, off_cs, off_ant, off_red, off_bar, off_tmem, total;
+};
+__host__ __device__ inline TcLayout tc_layout(int kpt) {
+  TcLayout L;
+  L.nbuf = kpt <= 160 ? 2 : 1;
+  L.npart = kpt <= 128 ? 2 : 1;
+  L.n_mn = L.nbuf;
+  L.n_k = kpt <= 128 ? 2 : 1;
+  L.col_dc = kpt;
+  L.col_v = 2 * kpt;
+  L.v_small = 32 * L.npart;
+  L.v_stride = L.v_small + 32;
+  L.col_qlo = L.col_v + L.nbuf * L.v_stride;      // + 32 nbuf <= 512 in every mode
+  L.sub_bytes = (uint32_t)kpt * 128u;
+  L.half_bytes = 2u * L.sub_bytes;
+  L.off_k = (uint32_t)L.n_mn * L.half_bytes;
+  L.off_clo = L.off_k + (uint32_t)L.n_k * L.half_bytes;
+  L.off_cs = L.off_clo + (uint32_t)((kpt + 31) / 32) * 128u * 128u;   // C lo: [chunks of 32 vectors][128 rows][128 B]
+  L.off_ant = L.off_cs + TcCfg::MS * 16;
+  L.off_red = L.off_ant + TcCfg::MS * 8;
+  L.off_bar = L.off_red + 8 * 16;                  // full_f[2], full_b[2], free[2], v[2], q[2], done
+  L.off_tmem = L.off_bar + 12 * 8;
+  L.total = L.off_tmem + 16;
+  return L;
+}
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -87,6 +105,14 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one lane of a converged warp: with elect.sync the compiler knows a single thread runs the guarded block and issues
+// tcgen05.mma / commit / bulk copies directly (behind `if (lane == 0)` it wraps EVERY such instruction in an ELECT retry loop,
+// ~90 cycles per MMA for the issuing thread -- measured, profiles/round2_ncu_hera350.md section 7)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -191,7 +217,13 @@ struct TcParams {
   const FitState* st;
   int nfp;
   unsigned int* dbg;    // mapped host memory: [0] = code of a wait that timed out, [1] tile, [2] CTA, [3] thread
+  long long* prof;      // development aid (CALB2_TC_PROF=<cta>): clock64 stamps of that CTA, [tile][TC_PROF_SLOTS]
+  int prof_cta;
 };
+constexpr int TC_PROF_SLOTS = 12, TC_PROF_TILES = 32;
+__device__ __forceinline__ void tc_stamp(const TcParams& p, int j, int slot) {
+  if (p.prof && (int)blockIdx.x == p.prof_cta && j < TC_PROF_TILES && (threadIdx.x & 31) == 0) p.prof[j * TC_PROF_SLOTS + slot] = clock64();
+}
 
 __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParams p) {
   using C = TcCfg;
@@ -202,23 +234,27 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   const int gsel = st->step & 1;
   const float* __restrict__ g_r = p.g_r[gsel];
   const float* __restrict__ g_i = p.g_i[gsel];
-
-  unsigned char* stage0 = smem + C::OFF_STAGE;
-  float* Clo = reinterpret_cast<float*>(smem + C::OFF_CLO);
-  ClassSlot* s_cs = reinterpret_cast<ClassSlot*>(smem + C::OFF_CS);
-  int2* s_ant = reinterpret_cast<int2*>(smem + C::OFF_ANT);
-  float* red = reinterpret_cast<float*>(smem + C::OFF_RED);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t *bar_full = bars, *bar_fullb = bars + 2, *bar_free = bars + 4, *bar_v = bars + 6, *bar_q = bars + 8;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kpt = mt.kp, nslots = mt.nslots;
+  const TcLayout L = tc_layout(kpt);
+
+  float* Clo = reinterpret_cast<float*>(smem + L.off_clo);
+  ClassSlot* s_cs = reinterpret_cast<ClassSlot*>(smem + L.off_cs);
+  int2* s_ant = reinterpret_cast<int2*>(smem + L.off_ant);
+  float* red = reinterpret_cast<float*>(smem + L.off_red);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  uint64_t *bar_full = bars, *bar_fullb = bars + 2, *bar_free = bars + 4, *bar_v = bars + 6, *bar_q = bars + 8, *bar_done = bars + 10;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int ntiles = mt.j1 - mt.j0;
-  const uint32_t sub_bytes = (uint32_t)kpt * 128u;       // one of the four copies of a tile
-  const uint32_t half_bytes = 2u * sub_bytes;            // the MN-major pair / the K-major pair
+  const uint32_t sub_bytes = L.sub_bytes, half_bytes = L.half_bytes;
   const float* Abase = p.At + mt.a_off + (size_t)mt.j0 * kpt * 4 * 32;
+  const size_t tile_floats = (size_t)kpt * 4 * 32;
   const bool mma_warp = warp == 8;
+  const int nbuf = L.nbuf, n_mn = L.n_mn, n_k = L.n_k;
+  // ring / buffer slot and barrier parity of tile j for a ring of n (1 or 2) entries
+  auto slot_of = [](int j, int n) { return n == 2 ? (j & 1) : 0; };
+  auto par_of = [](int j, int n) { return (uint32_t)(n == 2 ? (j >> 1) & 1 : j & 1); };
 
   if (mma_warp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
@@ -227,14 +263,15 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);  // full_f, full_b, free, v
       mbar_init(&bar_q[0], C::NEPI);  // two: a fast warp may arrive for tile j + 1 before a slow one has arrived for tile j
       mbar_init(&bar_q[1], C::NEPI);
+      mbar_init(bar_done, 1);
       mbar_fence_init();
-      for (int jj = 0; jj < 2 && jj < ntiles; ++jj) {
-        unsigned char* sb = stage0 + jj * C::STAGE_BYTES;
-        const float* src = Abase + (size_t)jj * kpt * 4 * 32;
+      for (int jj = 0; jj < n_mn && jj < ntiles; ++jj) {
         mbar_expect_tx(&bar_full[jj], half_bytes);
-        bulk_g2s(sb, src, half_bytes, &bar_full[jj]);
+        bulk_g2s(smem + jj * half_bytes, Abase + jj * tile_floats, half_bytes, &bar_full[jj]);
+      }
+      for (int jj = 0; jj < n_k && jj < ntiles; ++jj) {
         mbar_expect_tx(&bar_fullb[jj], half_bytes);
-        bulk_g2s(sb + half_bytes, src + 2 * kpt * 32, half_bytes, &bar_fullb[jj]);
+        bulk_g2s(smem + L.off_k + jj * half_bytes, Abase + jj * tile_floats + 2 * kpt * 32, half_bytes, &bar_fullb[jj]);
       }
     }
   }
@@ -273,7 +310,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
         // K-major SWIZZLE_128B: chunk of 32 k, row m, 16-byte pieces XOR-ed with (m & 7)
         Clo[(k >> 5) * 128 * 32 + m * 32 + (((((k & 31) >> 2) ^ (m & 7)) << 2) | (k & 3))] = c - hi[i];
       }
-      tmem_st8(tmem + tlane + C::COL_CHI + k0, hi);
+      tmem_st8(tmem + tlane + k0, hi);
     }
     tmem_st_wait();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // C lo was written by ordinary stores, the MMA reads it through the async proxy
@@ -284,39 +321,31 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
 
   if (mma_warp) {
     // =====================================================================================================================
-    // MMA / TMA warp: one thread issues everything
+    // MMA / TMA warp: the whole warp runs the control flow and the waits, one elected lane issues
     // =====================================================================================================================
-    if (lane == 0) {
-      const uint32_t idesc_f = umma_idesc_tf32(128, 32, 1);
-      const uint32_t idesc_b = umma_idesc_tf32(128, kpt, 0);
-      const uint32_t clo_addr = smem_u32(Clo);
-      const int nks = kpt / 8;
-      const int per = (nks + C::NPART - 1) / C::NPART;  // k-steps per partial V accumulator
-      uint32_t dc_accum = 0;
-      // phase F of tile jj into V buffer jj & 1:  V_p += C_hi . A_hi ;  V_small += C_hi . A_lo + C_lo . A_hi
-      // descriptor bases per stage; inside the loops only the 14-bit start-address field moves (units of 16 bytes)
-      uint64_t d_f_hi[2], d_f_lo[2], d_b_hi[2], d_b_lo[2];
-#pragma unroll
-      for (int sg = 0; sg < 2; ++sg) {
-        const uint32_t sbase = smem_u32(stage0 + sg * C::STAGE_BYTES);
-        d_f_hi[sg] = umma_desc_mn32(sbase);
-        d_f_lo[sg] = umma_desc_mn32(sbase + sub_bytes);
-        d_b_hi[sg] = umma_desc_k(sbase + 2u * sub_bytes);
-        d_b_lo[sg] = umma_desc_k(sbase + 3u * sub_bytes);
-      }
-      const uint64_t d_clo = umma_desc_k(clo_addr);
-      auto issue_f = [&](int jj) {
-        const int sg = jj & 1;
-        const uint32_t vcol = tmem + C::COL_V + C::V_STRIDE * sg;
-        tc_wait(&bar_full[sg], (jj >> 1) & 1, p.dbg, 1, jj);
-        tc_fence_after();
-        uint64_t b_hi = d_f_hi[sg], b_lo = d_f_lo[sg], a_lo = d_clo;
-        uint32_t a_hi = tmem + C::COL_CHI, vp = vcol;
+    const uint32_t idesc_f = umma_idesc_tf32(128, 32, 1);
+    const uint32_t idesc_b = umma_idesc_tf32(128, kpt, 0);
+    const int nks = kpt / 8;
+    const int per = (nks + L.npart - 1) / L.npart;  // k-steps per partial V accumulator
+    uint32_t dc_accum = 0;
+    const uint32_t mn_addr = smem_u32(smem), k_addr = smem_u32(smem + L.off_k);
+    const uint64_t d_clo = umma_desc_k(smem_u32(Clo));
+    // phase F of tile jj into its V buffer:  V_p += C_hi . A_hi ;  V_small += C_hi . A_lo + C_lo . A_hi
+    // (inside the loops only the 14-bit start-address field of a descriptor moves, in units of 16 bytes)
+    auto issue_f = [&](int jj) {
+      const int sg = slot_of(jj, n_mn);
+      const uint32_t vcol = tmem + L.col_v + L.v_stride * slot_of(jj, nbuf);
+      tc_wait(&bar_full[sg], par_of(jj, n_mn), p.dbg, 1, jj);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sbase = mn_addr + sg * half_bytes;
+        uint64_t b_hi = umma_desc_mn32(sbase), b_lo = umma_desc_mn32(sbase + sub_bytes), a_lo = d_clo;
+        uint32_t a_hi = tmem, vp = vcol;
         int in_part = 0;
         for (int ks = 0; ks < nks; ++ks) {
           umma_ts(vp, a_hi, b_hi, idesc_f, in_part ? 1u : 0u);
-          umma_ts(vcol + C::V_SMALL, a_hi, b_lo, idesc_f, ks ? 1u : 0u);
-          umma_ss(vcol + C::V_SMALL, a_lo, b_hi, idesc_f, 1u);
+          umma_ts(vcol + L.v_small, a_hi, b_lo, idesc_f, ks ? 1u : 0u);
+          umma_ss(vcol + L.v_small, a_lo, b_hi, idesc_f, 1u);
           b_hi += 64;   // 8 rows x 128 B = 1024 B
           b_lo += 64;
           a_hi += 8;
@@ -326,47 +355,67 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
             vp += 32;
           }
         }
-        umma_commit(&bar_v[sg]);
-      };
-      issue_f(0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int sg = j & 1;
-        unsigned char* sb = stage0 + sg * C::STAGE_BYTES;
-        if (j + 1 < ntiles) issue_f(j + 1);  // runs on the tensor cores while phase Q of tile j runs on the CUDA cores
-        if (j + 2 < ntiles) {  // phase F of tile j has retired: its MN-major pair can take tile j + 2 (a whole tile of lead time)
-          tc_wait(&bar_v[sg], (j >> 1) & 1, p.dbg, 6, j);
+        umma_commit(&bar_v[slot_of(jj, nbuf)]);
+      }
+      __syncwarp();
+    };
+    issue_f(0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int sk = slot_of(j, n_k), vb = slot_of(j, nbuf);
+      tc_stamp(p, j, 0);
+      // two V buffers: phase F of the next tile runs on the tensor cores while phase Q of this one runs on the CUDA cores
+      if (nbuf == 2 && j + 1 < ntiles) issue_f(j + 1);
+      tc_stamp(p, j, 1);
+      if (j + n_mn < ntiles) {  // phase F of tile j has retired: its MN-major pair takes tile j + n_mn
+        tc_wait(&bar_v[vb], par_of(j, nbuf), p.dbg, 6, j);
+        if (elect_one()) {
+          const int sg = slot_of(j, n_mn);
           mbar_expect_tx(&bar_full[sg], half_bytes);
-          bulk_g2s(sb, Abase + (size_t)(j + 2) * kpt * 4 * 32, half_bytes, &bar_full[sg]);
+          bulk_g2s(smem + sg * half_bytes, Abase + (size_t)(j + n_mn) * tile_floats, half_bytes, &bar_full[sg]);
         }
-        // ---- phase B once phase Q has written dL/dv: dC += Q_hi . A_hi^T + Q_hi . A_lo^T + Q_lo . A_hi^T
-        tc_wait(&bar_q[sg], (j >> 1) & 1, p.dbg, 2, j);
-        tc_wait(&bar_fullb[sg], (j >> 1) & 1, p.dbg, 7, j);
-        tc_fence_after();
-        const uint32_t qhi = tmem + C::COL_V + C::V_STRIDE * sg, qlo = tmem + C::COL_QLO + 32 * sg;
+        __syncwarp();
+      }
+      // ---- phase B once phase Q has written dL/dv: dC += Q_hi . A_hi^T + Q_hi . A_lo^T + Q_lo . A_hi^T
+      tc_wait(&bar_q[vb], par_of(j, nbuf), p.dbg, 2, j);
+      tc_wait(&bar_fullb[sk], par_of(j, n_k), p.dbg, 7, j);
+      tc_fence_after();
+      tc_stamp(p, j, 2);
+      if (elect_one()) {
+        const uint32_t sbase = k_addr + sk * half_bytes;
+        const uint64_t d_b_hi = umma_desc_k(sbase), d_b_lo = umma_desc_k(sbase + sub_bytes);
+        const uint32_t qhi = tmem + L.col_v + L.v_stride * vb, qlo = tmem + L.col_qlo + 32 * vb;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t b_hi = d_b_hi[sg] + 2 * ks, b_lo = d_b_lo[sg] + 2 * ks;  // 32 B along the 128 B row
-          umma_ts(tmem + C::COL_DC, qhi + 8 * ks, b_hi, idesc_b, dc_accum);
-          dc_accum = 1u;
-          umma_ts(tmem + C::COL_DC, qhi + 8 * ks, b_lo, idesc_b, 1u);
-          umma_ts(tmem + C::COL_DC, qlo + 8 * ks, b_hi, idesc_b, 1u);
+          const uint64_t b_hi = d_b_hi + 2 * ks, b_lo = d_b_lo + 2 * ks;  // 32 B along the 128 B row
+          umma_ts(tmem + L.col_dc, qhi + 8 * ks, b_hi, idesc_b, ks ? 1u : dc_accum);
+          umma_ts(tmem + L.col_dc, qhi + 8 * ks, b_lo, idesc_b, 1u);
+          umma_ts(tmem + L.col_dc, qlo + 8 * ks, b_hi, idesc_b, 1u);
         }
-        umma_commit(&bar_free[sg]);
-        if (j + 2 < ntiles) {  // the K-major pair is free once phase B has retired; tile j + 2 needs it two tiles from now
-          tc_wait(&bar_free[sg], (j >> 1) & 1, p.dbg, 3, j);
-          mbar_expect_tx(&bar_fullb[sg], half_bytes);
-          bulk_g2s(sb + half_bytes, Abase + (size_t)(j + 2) * kpt * 4 * 32 + 2 * kpt * 32, half_bytes, &bar_fullb[sg]);
-        }
+        umma_commit(&bar_free[sk]);
+        // the accumulator is final after the last phase B.  (Its own barrier: with a one-entry ring the parity of free[] repeats
+        // every two tiles, and a phase-Q warp can get here while phase B of the tile before the last is still in flight.)
+        if (j == ntiles - 1) umma_commit(bar_done);
       }
+      __syncwarp();
+      dc_accum = 1u;
+      tc_stamp(p, j, 3);
+      // one V buffer: the next phase F goes behind this phase B in the tensor pipe (its operands landed during phase Q)
+      if (nbuf == 1 && j + 1 < ntiles) issue_f(j + 1);
+      if (j + n_k < ntiles) {  // the K-major pair is free once phase B has retired
+        tc_wait(&bar_free[sk], par_of(j, n_k), p.dbg, 3, j);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_fullb[sk], half_bytes);
+          bulk_g2s(smem + L.off_k + sk * half_bytes, Abase + (size_t)(j + n_k) * tile_floats + 2 * kpt * 32, half_bytes, &bar_fullb[sk]);
+        }
+        __syncwarp();
+      }
+      tc_stamp(p, j, 4);
     }
-    __syncwarp();
   } else {
     // =====================================================================================================================
     // phase-Q warps
     // =====================================================================================================================
-    const int nks = kpt / 8;
-    const int per = (nks + C::NPART - 1) / C::NPART;
-    const int npart = (nks + per - 1) / per;
+    const int npart = L.npart;
     const int cbase = 16 * half;        // this warp's columns of the tile
     const int mycol = cbase + 8 * part; // the 8 channels this thread does the arithmetic for
     const ClassSlot cs = s_cs[s];
@@ -391,6 +440,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
     if (valid) load_inputs(0, nx);
     for (int j = 0; j < ntiles; ++j) {
       const int f0 = (mt.j0 + j) * C::FT + mycol;
+      const int vb = slot_of(j, nbuf);
       if (valid) {
 #pragma unroll
         for (int a = 0; a < 7; ++a) {
@@ -399,9 +449,11 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
         }
         if (j + 1 < ntiles) load_inputs(j + 1, nx);
       }
-      const uint32_t vcol = tmem + tlane + C::COL_V + C::V_STRIDE * (j & 1) + cbase;
-      tc_wait(&bar_v[j & 1], (j >> 1) & 1, p.dbg, 4, j);
+      const uint32_t vcol = tmem + tlane + L.col_v + L.v_stride * vb + cbase;
+      if (tid == 0) tc_stamp(p, j, 6);
+      tc_wait(&bar_v[vb], par_of(j, nbuf), p.dbg, 4, j);
       tc_fence_after();
+      if (tid == 0) tc_stamp(p, j, 7);
       // V row of this thread, 16 columns: partial accumulators + the small terms, added with round-to-nearest
       float v[16], t[16];
       tmem_ld16(vcol, v);
@@ -410,9 +462,10 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += t[i];
       }
-      tmem_ld16(vcol + C::V_SMALL, t);
+      tmem_ld16(vcol + L.v_small, t);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] += t[i];
+      if (tid == 0) tc_stamp(p, j, 8);
       // pair re / im: lane 2g holds v_r of group g, lane 2g + 1 its v_i; each takes 8 of the 16 channels
       float vr[8], vi[8];
 #pragma unroll
@@ -451,6 +504,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
 #pragma unroll
         for (int i = 0; i < 4; ++i) zdst[i] = make_float4(zz[2 * i].x, zz[2 * i].y, zz[2 * i + 1].x, zz[2 * i + 1].y);
       }
+      if (tid == 0) tc_stamp(p, j, 9);
       // back to rows: lane 2g needs q_r of all 16 columns, lane 2g + 1 q_i
       float row[16], hi[16], lo[16];
 #pragma unroll
@@ -466,21 +520,22 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
         lo[i] = row[i] - hi[i];
       }
       tmem_st16(vcol, hi);  // over partial 0 of this tile's V buffer: these lanes / columns are read by this warp only
-      tmem_st16(tmem + tlane + C::COL_QLO + 32 * (j & 1) + cbase, lo);
+      tmem_st16(tmem + tlane + L.col_qlo + 32 * vb + cbase, lo);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive_plain(&bar_q[j & 1]);
+      mbar_arrive_plain(&bar_q[vb]);
+      if (tid == 0) tc_stamp(p, j, 10);
     }
     // ---- backward sums: wait for the last phase B, then row m of dC -> dcpart
     {
       const int last = ntiles - 1;
-      tc_wait(&bar_free[last & 1], (last >> 1) & 1, p.dbg, 5, last);
+      tc_wait(bar_done, 0, p.dbg, 5, last);
       tc_fence_after();
       float* dst = p.dcpart + (size_t)mt.seg * p.dc_plane + (size_t)cs.row0 * 2 + part;
       const int k_lo = half * (kpt / 2), k_hi = k_lo + kpt / 2;
       for (int k0 = k_lo; k0 < k_hi; k0 += 8) {
         float d8[8];
-        tmem_ld8(tmem + tlane + C::COL_DC + k0, d8);  // .sync.aligned: the whole warp, also the lanes of missing groups
+        tmem_ld8(tmem + tlane + L.col_dc + k0, d8);  // .sync.aligned: the whole warp, also the lanes of missing groups
         if (valid) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)

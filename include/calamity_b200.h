@@ -165,6 +165,9 @@ int calb2_debug_check_guards(int64_t* nbuffers, int64_t* nviolations);
 /* Development aid: the 16-word progress / time-out record of the tensor-core kernel (mapped host memory; readable while
  * another thread is blocked in a CUDA call). */
 int calb2_debug_tc_record(uint32_t* out16);
+/* Development aid: with CALB2_TC_PROF=<cta> set at plan creation, the SM-clock stamps of that CTA of the last tensor-core
+ * launch, [32 tiles][12 slots] (slots: calfit_tc.cuh, tc_stamp). */
+int calb2_debug_tc_profile(calb2_plan* plan, int64_t* out, int32_t n);
 
 /* Once per calibrate_and_model_tensor call: mirrors calibration.py:1143-1152. */
 int calb2_plan_create(const calb2_plan_desc* desc, calb2_plan** out);

@@ -13,8 +13,8 @@ from tests.helpers import flat_from_synth, long_baseline_subset, mixed_problem, 
 pytestmark = pytest.mark.gpu
 F = np.float64
 # the device paths: the streaming kernel (one private basis copy per group); the shared-basis path as shipped (each distinct
-# basis stored once, automatic for classes of >= 4 groups: classes of <= 128 vectors on the tensor cores, calfit_tc.cuh, the
-# rest on the CUDA-core shapes of calfit_shared.cuh); and the shared-basis path with the tensor-core shape switched off
+# basis stored once, automatic for classes of >= 4 groups: on the tensor cores, calfit_tc.cuh; multi-baseline slots and
+# the 'sum' regulariser on the CUDA-core shapes of calfit_shared.cuh); and the shared-basis path with the tensor-core shape switched off
 PATHS = [pytest.param(dict(shared_basis=-1), id="stream"), pytest.param(dict(shared_basis=0), id="shared"),
          pytest.param(dict(shared_basis=0, tc=False), id="shared-cuda-cores")]
 
@@ -25,10 +25,12 @@ def _plan(p, tc=True, **kw):
     from calamity_b200.fitter import FitPlan
 
     os.environ["CALB2_TC"] = "1" if tc else "0"  # read by calb2_plan_create
+    os.environ["CALB2_TC_MIN"] = "1"  # small test classes too (the default keeps classes of < 16 groups on the CUDA cores)
     try:
         plan = FitPlan(p.lay, device=0, **kw)
     finally:
         os.environ.pop("CALB2_TC", None)
+        os.environ.pop("CALB2_TC_MIN", None)
     if kw.get("shared_basis", 0) >= 0:
         assert (plan.info["n_tc_ctas"] > 0) == tc
     plan.set_integration(p.data_r, p.data_i, p.wgts)

@@ -19,10 +19,12 @@ def _plan(p, tc=True, **kw):
     from calamity_b200.fitter import FitPlan
 
     os.environ["CALB2_TC"] = "1" if tc else "0"  # read by calb2_plan_create: tensor-core shape on (default) / off
+    os.environ["CALB2_TC_MIN"] = "1"  # small test classes too (the default keeps classes of < 16 groups on the CUDA cores)
     try:
         plan = FitPlan(p.lay, device=0, **kw)
     finally:
         os.environ.pop("CALB2_TC", None)
+        os.environ.pop("CALB2_TC_MIN", None)
     plan.set_integration(p.data_r, p.data_i, p.wgts)
     plan.set_gains(p.g0_r, p.g0_i)
     plan.set_coeffs(p.c0_r, p.c0_i)

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const Params p) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const int K = p.K, N = p.N;
   const bool b_mn = (p.test == 2 || p.test == 3 || p.test == 5 || p.test == 6);  // B tile is [K rows][32 n] (MN-major operand)
-  const bool ts = (p.test >= 3 && p.test <= 6);
+  const bool ts = (p.test >= 3 && p.test <= 6) || p.test == 8;
+  const bool k_b32 = p.test == 8;  // K-major operand read out of the MN-major operand's layout (32-byte-base swizzle): one copy for both?
   const bool split = (p.test == 5 || p.test == 6);
   const bool raw_hi = (p.test == 6);  // hi operand = the unmodified float: does the tensor core truncate it to tf32 itself?
 
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const Params p) {
     const int r = e >> 5, c = e & 31;
     const float x = r < brows ? p.B[r * 32 + c] : 0.f;
     const float hi = split ? tf32_hi(x) : x;
-    const int pos = b_mn ? sw128_b32(r, c) : sw128(r, c);
+    const int pos = (b_mn || k_b32) ? sw128_b32(r, c) : sw128(r, c);
     sB[pos] = raw_hi ? x : hi;
     sBlo[pos] = split ? (x - hi) : 0.f;
   }
@@ -179,6 +180,9 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const Params p) {
         if (b_mn) {  // rows k .. k+7 of the tile = two 4-row atoms of the 32B-base swizzle, 512 B apart (SBO)
           bdesc = smem_desc(sb_addr + (uint32_t)k * 128u, 512, 512, 1);
           bdesc_lo = smem_desc(sblo_addr + (uint32_t)k * 128u, 512, 512, 1);
+        } else if (k_b32) {
+          bdesc = smem_desc(sb_addr + (uint32_t)k * 4u, 16, 1024, 1);
+          bdesc_lo = bdesc;
         } else {     // K-major: N rows, 8 k = 32 B inside the 128 B row
           bdesc = smem_desc_sw128(sb_addr + (uint32_t)k * 4u, 16, 1024);
           bdesc_lo = smem_desc_sw128(sblo_addr + (uint32_t)k * 4u, 16, 1024);
@@ -217,8 +221,16 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const Params p) {
 }
 
 // Cycles per tcgen05.mma (issue to retire, `reps` back to back): form 0 = TS, B MN-major N=32; 1 = SS (A K-major), B MN-major N=32;
-// 2 = TS, B K-major N=n; 3 = TS, B MN-major N=64 (two 32-column blocks, LBO)
-__global__ void __launch_bounds__(128, 1) time_kernel(int form, int n, int reps, long long* out) {
+// 2 = TS, B K-major N=n; 3 = TS, B MN-major N=64 (two 32-column blocks, LBO); 4-7: accumulator / operand reuse variants
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// (issued behind elect.sync by a converged warp: behind `if (tid == 0)` the compiler wraps every tcgen05.mma in an ELECT retry
+// loop and the measurement shows the issuing thread's ~90-170 cycles per MMA, not the tensor pipe)
+template <int form>
+__global__ void __launch_bounds__(128, 1) time_kernel(int n, int reps, long long* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t s_tmem;
@@ -237,23 +249,33 @@ __global__ void __launch_bounds__(128, 1) time_kernel(int form, int n, int reps,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  if (tid == 0) {
+  if (__shfl_sync(0xffffffffu, warp, 0) == 0) {
+   long long t0 = 0, t1 = 0;
+   if (elect_one()) {
     const uint32_t sb = smem_u32(smem);
     const uint64_t b_mn = smem_desc(sb, 8192, 512, 1), b_k = smem_desc_sw128(sb, 16, 1024), a_k = smem_desc_sw128(sb + 65536, 16, 1024);
     const uint32_t id32 = idesc_tf32(128, 32, 0, 1), id64 = idesc_tf32(128, 64, 0, 1), idn = idesc_tf32(128, n, 0, 0);
-    const long long t0 = clock64();
+    t0 = clock64();
     for (int r = 0; r < reps; ++r) {
       if (form == 0) mma_ts(tmem + 256, tmem + (r & 15) * 8, b_mn + (uint64_t)((r & 7) * 64), id32, 1);
       else if (form == 1) mma_ss(tmem + 256, a_k + (uint64_t)((r & 3) * 2), b_mn + (uint64_t)((r & 7) * 64), id32, 1);
       else if (form == 2) mma_ts(tmem + 256, tmem + (r & 3) * 8, b_k + (uint64_t)((r & 3) * 2), idn, 1);
-      else mma_ts(tmem + 256, tmem + (r & 15) * 8, b_mn + (uint64_t)((r & 7) * 64), id64, 1);
+      else if (form == 3) mma_ts(tmem + 256, tmem + (r & 15) * 8, b_mn + (uint64_t)((r & 7) * 64), id64, 1);
+      else if (form == 4) mma_ts(tmem + 256 + 32 * (r & 3), tmem + (r & 15) * 8, b_mn + (uint64_t)((r & 7) * 64), id32, 1);  // 4 accumulators
+      else if (form == 5) mma_ts(tmem + 256 + 128 * (r & 1), tmem + (r & 3) * 8, b_k + (uint64_t)((r & 3) * 2), idn, 1);       // 2 accumulators
+      else if (form == 6) mma_ts(tmem + 256, tmem + (r & 15) * 8, b_mn + (uint64_t)((r & 7) * 64), id32, r & 7 ? 1 : 0);      // restart every 8
+      else mma_ts(tmem + 256, tmem, b_mn, id32, 1);  // same operands every time
     }
-    const long long t1 = clock64();
+    t1 = clock64();
     mma_commit(&bar);
-    mbar_wait(&bar, 0);
-    const long long t2 = clock64();
-    out[0] = t1 - t0;
-    out[1] = t2 - t0;
+   }
+   __syncwarp();
+   mbar_wait(&bar, 0);
+   const long long t2 = clock64();
+   if (t0) {
+     out[0] = t1 - t0;
+     out[1] = t2 - t0;
+   }
   }
   __syncthreads();
   tc_fence_before();
@@ -283,7 +305,10 @@ int main() {
                         {6, 208, 32, "T6 TS  3xTF32 split, hi operands = raw floats (hardware truncation) (K=208, N=32)"},
                         {1, 32, 104, "T1 SS  K-major / K-major (K=32, N=104)"},
                         {1, 32, 32, "T1 SS  K-major / K-major (K=32, N=32)"},
-                        {2, 8, 32, "T2 SS  A K-major . B MN-major  (K=8, N=32)"}};
+                        {2, 8, 32, "T2 SS  A K-major . B MN-major  (K=8, N=32)"},
+                        {8, 8, 128, "T8 TS  B K-major read from the 32B-base-swizzled (MN-major) layout (K=8, N=128)"},
+                        {8, 32, 208, "T8 TS  B K-major read from the 32B-base-swizzled (MN-major) layout (K=32, N=208)"},
+                        {8, 32, 128, "T8 TS  B K-major read from the 32B-base-swizzled (MN-major) layout (K=32, N=128)"}};
   int bad = 0;
   for (const Case& cs : cases) {
     const int K = cs.K, N = cs.N;
@@ -315,7 +340,7 @@ int main() {
     for (int m = 0; m < 128; ++m)
       for (int n = 0; n < ncols; ++n) {
         double ref = 0;
-        for (int k = 0; k < (b_mn ? K : 32); ++k) ref += (double)A[m * K + k] * (double)(b_mn ? B[k * 32 + n] : B[n * 32 + k]);
+        for (int k = 0; k < K; ++k) ref += (double)A[m * K + k] * (double)(b_mn ? B[k * 32 + n] : B[n * 32 + k]);
         maxerr = std::max(maxerr, std::abs(ref - (double)D[m * ncols + n]));
         maxref = std::max(maxref, std::abs(ref));
       }
@@ -329,7 +354,7 @@ int main() {
       printf("    nonzero outputs: %d of %zu; D[0][0..3] = %g %g %g %g; D[5][0..3] = %g %g %g %g\n", nz, D.size(), D[0], D[1], D[2], D[3],
              D[5 * ncols], D[5 * ncols + 1], D[5 * ncols + 2], D[5 * ncols + 3]);
       double r0 = 0, r1 = 0;
-      for (int k = 0; k < (b_mn ? K : 32); ++k) {
+      for (int k = 0; k < K; ++k) {
         r0 += (double)A[k] * (double)(b_mn ? B[k * 32 + 0] : B[k]);
         r1 += (double)A[k] * (double)(b_mn ? B[k * 32 + 1] : B[32 + k]);
       }
@@ -342,13 +367,17 @@ int main() {
   {
     long long* dout;
     CK(cudaMalloc(&dout, 16));
-    CK(cudaFuncSetAttribute(time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180224));
+    typedef void (*TimeFn)(int, int, long long*);
+    const TimeFn fns[8] = {time_kernel<0>, time_kernel<1>, time_kernel<2>, time_kernel<3>, time_kernel<4>, time_kernel<5>, time_kernel<6>, time_kernel<7>};
+    for (TimeFn f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 180224));
     struct TCase { int form, n; const char* name; };
     const TCase tcs[] = {{0, 32, "TS  B MN-major  N=32"}, {1, 32, "SS  B MN-major  N=32"}, {3, 64, "TS  B MN-major  N=64"},
-                         {2, 16, "TS  B K-major   N=16"}, {2, 64, "TS  B K-major   N=64"}, {2, 128, "TS  B K-major   N=128"}};
+                         {2, 16, "TS  B K-major   N=16"}, {2, 64, "TS  B K-major   N=64"}, {2, 128, "TS  B K-major   N=128"},
+                         {4, 32, "TS  MN N=32, 4 accum"}, {5, 128, "TS  K N=128, 2 accum"}, {6, 32, "TS  MN N=32, restart/8"},
+                         {7, 32, "TS  MN N=32, same ops"}};
     for (const TCase& tc : tcs)
       for (int reps : {64, 512}) {
-        time_kernel<<<1, 128, 180224>>>(tc.form, tc.n, reps, dout);
+        fns[tc.form]<<<1, 128, 180224>>>(tc.n, reps, dout);
         CK(cudaDeviceSynchronize());
         long long h[2];
         CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));

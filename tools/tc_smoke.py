@@ -50,6 +50,17 @@ def run(name, nsel):
     print(f"{name}: tc ctas {info['n_tc_ctas']} tc slots {info['n_tc_slots']}/{info['nslots_total']}  loss {float(loss):.7e} oracle {float(ol):.7e} "
           f"rel {abs(float(loss) - float(ol)) / abs(float(ol)):.2e}  grads g {rel_err(dgr, ogr):.2e} {rel_err(dgi, ogi):.2e} "
           f"c {rel_err(dcr, ocr):.2e} {rel_err(dci, oci):.2e}", flush=True)
+    if os.environ.get("CALB2_TC_PROF"):
+        buf = (ctypes.c_int64 * (32 * 12))()
+        nat.check(nat.load().calb2_debug_tc_profile(plan._handle, buf, 32 * 12))
+        a = np.array(buf, dtype=np.int64).reshape(32, 12)
+        t0 = a[0, 0]
+        print("   stamps (cycles since tile 0 start): mma[before F(j+1), after issue, after wait q, after B issue, after refill] | "
+              "q[before wait v, after, V loaded, computed, arrived]")
+        for j in range(32):
+            if a[j, 0] == 0:
+                break
+            print(f"   tile {j:2d}: mma {[int(x - t0) if x else -1 for x in a[j, 0:5]]}  q {[int(x - t0) if x else -1 for x in a[j, 6:11]]}")
     hist, res = plan.fit(optimizer="Adamax", maxsteps=30, tol=0.0, learning_rate=1e-2)
     o = rp.fit(p.g0_r, p.g0_i, p.c0_r, p.c0_i, p.data_r, p.data_i, p.wgts, optimizer="Adamax", maxsteps=30, tol=0.0, learning_rate=1e-2)
     ref = np.asarray(o[4]["loss"], dtype=F)
