@@ -478,6 +478,10 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
     tp.dbg = pl->tc_dbg;
     tp.prof = pl->tc_prof.p;
     tp.prof_cta = pl->tc_prof_cta;
+    {
+      static const int flags = getenv("CALB2_TC_FLAGS") ? atoi(getenv("CALB2_TC_FLAGS")) : 0;  // measured best at HERA-350
+      tp.flags = flags;
+    }
     static bool configured[MAX_DEVICES] = {};
     const int dev = current_device();
     if (!configured[dev]) {
@@ -1345,13 +1349,14 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   {
     // tensor-core shape: on by default for single-baseline slots; CALB2_TC=0 keeps every class on the CUDA-core shapes
     pl->tc_enabled = pl->cls_single_bl && !(getenv("CALB2_TC") && atoi(getenv("CALB2_TC")) == 0);
-    // a tensor-core CTA costs the same for 1 or 64 groups (128 accumulator rows): classes with fewer than tc_min members stay
-    // on the CUDA-core shapes (32 / 64 groups per CTA, cost by 8-group block)
+    // a tensor-core CTA costs the same for 1 or 64 groups (128 accumulator rows): classes of up to 128 vectors with fewer than
+    // tc_min members stay on the CUDA-core shapes (32 / 64 groups per CTA, cost by 8-group block).  Larger classes always go to
+    // the tensor cores: a handful of them on the large CUDA-core shape took 435 us at HERA-350, next to a 650 us pass.
     int tc_min = 16;
     if (getenv("CALB2_TC_MIN")) tc_min = std::max(1, atoi(getenv("CALB2_TC_MIN")));
     long long tc_off = 0;
     for (auto& ci : pl->classes) {
-      if (!pl->tc_enabled || ci.nmembers < tc_min) ci.tc = false;
+      if (!pl->tc_enabled || (ci.nmembers < tc_min && ci.kpt <= 128)) ci.tc = false;
       if (ci.tc) {
         ci.tc_off = tc_off;
         tc_off += (long long)pl->ntiles_c * 4 * ci.kpt * SHARED_FT;

@@ -26,9 +26,9 @@
 // free again once phase F retired, the second only after phase B; one copy cannot serve both, the K-major descriptor does not
 // take the 32-byte-base swizzle: tools/tc_probe.cu T8).
 //
-// One warp issues the MMAs and the bulk copies (one elected lane), eight warps do phase Q; mbarriers connect them:
+// One warp issues the MMAs, one the bulk copies (an elected lane each), eight warps do phase Q; mbarriers connect them:
 //   full_f[s] / full_b[s]  tile pair landed (TMA) -> MMA warp      free[s]  phase B retired (tcgen05.commit) -> K-major refill;  done -> epilogue
-//   v[b]     phase F retired (commit)     -> phase-Q warps, MN-major refill      q[b]  phase Q done (256 arrivals) -> MMA warp issues B
+//   v[b]     phase F retired (commit)     -> phase-Q warps, MN-major refill      q[b]  phase Q done (8 warp arrivals) -> MMA warp issues B
 // The tensor pipe executes in issue order, so B(j) reads dL/dv(j) out of its V buffer before the next phase F into that buffer
 // overwrites it.  Descriptor encodings follow cute/arch/mma_sm100_desc.hpp; every operand form used here is checked by
 // tools/tc_probe.cu.
@@ -41,7 +41,7 @@ struct TcCfg {
   static constexpr int MS = 64, FT = 32;
   static constexpr int KPMAX = 208;                          // rows per class tile (ncomp rounded up to 16)
   static constexpr int NEPI = 256;                           // 8 phase-Q warps: TMEM lane quadrant = warp & 3, column half = warp >> 2
-  static constexpr int NTHR = NEPI + 32;                     // + the MMA / TMA warp
+  static constexpr int NTHR = NEPI + 64;                     // + the MMA warp (8) and the TMA warp (9)
   static constexpr int NPART_MAX = 2;
 };
 
@@ -71,7 +71,7 @@ __host__ __device__ inline TcLayout tc_layout(int kpt) {
   L.off_ant = L.off_cs + TcCfg::MS * 16;
   L.off_red = L.off_ant + TcCfg::MS * 8;
   L.off_bar = L.off_red + 8 * 16;                  // full_f[2], full_b[2], free[2], v[2], q[2], done
-  L.off_tmem = L.off_bar + 12 * 8;
+  L.off_tmem = L.off_bar + 14 * 8;
   L.total = L.off_tmem + 16;
   return L;
 }
@@ -152,42 +152,62 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): a thread's 8 consecutive channels in ONE instruction -- half the L1
+// wavefronts of two 128-bit accesses for the per-baseline rows, whose lanes all sit in different 128-byte lines
+struct alignas(32) f32x8 { float v[8]; };
+__device__ __forceinline__ f32x8 ldg256(const float* ptr) {
+  f32x8 r;
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(ptr));
+  return r;
+}
+__device__ __forceinline__ void stg256(float* ptr, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f),
+               "f"(g), "f"(h) : "memory");
+}
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ void mbar_arrive_plain(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Bounded wait: a protocol error must not hang the GPU.  mbarrier.try_wait suspends the thread in hardware (cheap, no polling
-// traffic); every 16th return without completion the waiter looks at the clock, and after 4 s records (code, tile, CTA, thread)
-// in a mapped host buffer and traps; calb2 reports the record with the CUDA error.
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned int code, int j) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  unsigned int polls = 0;
-  unsigned long long t0 = 0;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((++polls & 15u) == 0u) {
-      const unsigned long long now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 4000000000ull) {
-        if (dbg) {
-          dbg[1] = (unsigned int)j;
-          dbg[2] = blockIdx.x;
-          dbg[3] = threadIdx.x;
-          __threadfence_system();
-          dbg[0] = code;
-          __threadfence_system();
+// Bounded wait: a protocol error must not hang the GPU.  mbarrier.try_wait suspends the thread in hardware (with a long
+// suspend-time hint: no polling traffic, no issue slots taken); every 4th return without completion the waiter looks at the SM clock (clock64: a register read -- %globaltimer
+// costs thousands of cycles per read and stretched every long wait, profiles/round2_ncu_hera350.md section 7), and after
+// ~5 s records (code, tile, CTA, thread) in a mapped host buffer and traps; calb2 reports the record with the CUDA error.
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned int code, int j, bool lane0_only = false) {
+  // called by converged warps; lane0_only: lane 0 polls, the warp re-converges behind it
+  if (!lane0_only || (threadIdx.x & 31) == 0) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    unsigned int polls = 0;
+    long long t0 = 0;
+    for (;;) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware until the phase completes -- a spinning
+                                                    // waiter takes issue slots from the phase-Q warps of its scheduler (measured)
+          : "memory");
+      if (done) break;
+      if ((++polls & 3u) == 0u) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 10000000000ll) {
+          if (dbg) {
+            dbg[1] = (unsigned int)j;
+            dbg[2] = blockIdx.x;
+            dbg[3] = threadIdx.x;
+            __threadfence_system();
+            dbg[0] = code;
+            __threadfence_system();
+          }
+          __trap();
         }
-        __trap();
       }
     }
   }
+  __syncwarp();
 }
 
 __device__ __forceinline__ void tc_mark(unsigned int* dbg, int slot, unsigned int value) {
@@ -219,8 +239,9 @@ struct TcParams {
   unsigned int* dbg;    // mapped host memory: [0] = code of a wait that timed out, [1] tile, [2] CTA, [3] thread
   long long* prof;      // development aid (CALB2_TC_PROF=<cta>): clock64 stamps of that CTA, [tile][TC_PROF_SLOTS]
   int prof_cta;
+  int flags;            // development switches (CALB2_TC_FLAGS): 1 lane-0 polling, 2 L2 row prefetch, 4 clock-paced issue, 8 phase B first when ready
 };
-constexpr int TC_PROF_SLOTS = 12, TC_PROF_TILES = 32;
+constexpr int TC_PROF_SLOTS = 24, TC_PROF_TILES = 32;  // 0-4 MMA warp, 6-10 phase-Q warp 0, 12-19 arrival of each phase-Q warp, 20-22 (tile 0) start / prologue / end
 __device__ __forceinline__ void tc_stamp(const TcParams& p, int j, int slot) {
   if (p.prof && (int)blockIdx.x == p.prof_cta && j < TC_PROF_TILES && (threadIdx.x & 31) == 0) p.prof[j * TC_PROF_SLOTS + slot] = clock64();
 }
@@ -236,6 +257,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   const float* __restrict__ g_i = p.g_i[gsel];
   const int kpt = mt.kp, nslots = mt.nslots;
   const TcLayout L = tc_layout(kpt);
+  const bool l0 = p.flags & 1, use_prefetch = p.flags & 2, use_pace = p.flags & 4, b_first = p.flags & 8;
 
   float* Clo = reinterpret_cast<float*>(smem + L.off_clo);
   ClassSlot* s_cs = reinterpret_cast<ClassSlot*>(smem + L.off_cs);
@@ -246,11 +268,16 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) tc_stamp(p, 0, 20);
   const int ntiles = mt.j1 - mt.j0;
   const uint32_t sub_bytes = L.sub_bytes, half_bytes = L.half_bytes;
   const float* Abase = p.At + mt.a_off + (size_t)mt.j0 * kpt * 4 * 32;
   const size_t tile_floats = (size_t)kpt * 4 * 32;
-  const bool mma_warp = warp == 8;
+#ifdef CALB2_TC_SWAP_ROLES
+  const bool mma_warp = warp == 9, tma_warp = warp == 8;
+#else
+  const bool mma_warp = warp == 8, tma_warp = warp == 9;
+#endif
   const int nbuf = L.nbuf, n_mn = L.n_mn, n_k = L.n_k;
   // ring / buffer slot and barrier parity of tile j for a ring of n (1 or 2) entries
   auto slot_of = [](int j, int n) { return n == 2 ? (j & 1) : 0; };
@@ -261,8 +288,10 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if (lane == 0) {
       for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);  // full_f, full_b, free, v
-      mbar_init(&bar_q[0], C::NEPI);  // two: a fast warp may arrive for tile j + 1 before a slow one has arrived for tile j
-      mbar_init(&bar_q[1], C::NEPI);
+      // two: a fast warp may arrive for tile j + 1 before a slow one has arrived for tile j.  One arrival per WARP: every arrival
+      // wakes the waiters sleeping on the CTA's barriers, and 256 of them per tile kept the MMA / TMA warps polling (measured)
+      mbar_init(&bar_q[0], C::NEPI / 32);
+      mbar_init(&bar_q[1], C::NEPI / 32);
       mbar_init(bar_done, 1);
       mbar_fence_init();
       for (int jj = 0; jj < n_mn && jj < ntiles; ++jj) {
@@ -294,22 +323,56 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   const int quad = warp & 3, half = (warp >> 2) & 1;
   const int m = quad * 32 + lane, s = m >> 1, part = m & 1;
   const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-  const bool valid = !mma_warp && s < nslots;
+  const bool q_warp = warp < 8;
+  const bool valid = q_warp && s < nslots;
 
   // ---- coefficients: hi part -> TMEM (the A-operand of phase F for the whole pass), lo part -> shared memory operand
-  if (!mma_warp) {
-    const float* src = (part ? p.c_i : p.c_r) + s_cs[s].coef0;
+  if (q_warp) {
+    // pass 1, coalesced: warp w brings rows 16 w .. 16 w + 15 (a group's coefficients are contiguous: lanes run over the vectors)
+    // into the C lo buffer, already at their K-major SWIZZLE_128B positions (chunk of 32 vectors, row m, 16-byte pieces XOR-ed
+    // with m & 7).  Lane-per-row loads cost 32 L1 wavefronts per instruction and made this prologue 17 000 cycles long.
+    // (eight rows at a time: all their loads are issued before the first value is used)
+    for (int r0 = 0; r0 < 16; r0 += 8) {
+      float c[8][7];  // kpt <= 208: at most 7 chunks of 32 vectors
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int mm = warp * 16 + r0 + r, ss = mm >> 1;
+        const bool ok = ss < nslots;
+        const float* src = ((mm & 1) ? p.c_i : p.c_r) + s_cs[ss].coef0;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const int k = lane + 32 * q;
+          c[r][q] = (ok && k < mt.ncomp) ? src[k] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int mm = warp * 16 + r0 + r;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const int k = lane + 32 * q;
+          if (k < kpt) Clo[q * 128 * 32 + mm * 32 + ((((lane >> 2) ^ (mm & 7)) << 2) | (lane & 3))] = c[r][q];
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight phase-Q warps
+    // pass 2: thread (row m, half) splits its half of the row: hi -> TMEM (phase F's A-operand), lo stays in place
     const int k_lo = half * (kpt / 2), k_hi = k_lo + kpt / 2;  // kpt / 2 is a multiple of 8
     for (int k0 = k_lo; k0 < k_hi; k0 += 8) {
-      float hi[8];
+      float* row = Clo + (k0 >> 5) * 128 * 32 + m * 32;
+      const int c16 = (k0 & 31) >> 2;
+      float4* p0 = reinterpret_cast<float4*>(row + ((c16 ^ (m & 7)) << 2));
+      float4* p1 = reinterpret_cast<float4*>(row + (((c16 + 1) ^ (m & 7)) << 2));
+      const float4 a = *p0, b = *p1;
+      const float c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float hi[8], lo[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int k = k0 + i;
-        const float c = (valid && k < mt.ncomp) ? src[k] : 0.f;
-        hi[i] = tf32_trunc(c);
-        // K-major SWIZZLE_128B: chunk of 32 k, row m, 16-byte pieces XOR-ed with (m & 7)
-        Clo[(k >> 5) * 128 * 32 + m * 32 + (((((k & 31) >> 2) ^ (m & 7)) << 2) | (k & 3))] = c - hi[i];
+        hi[i] = tf32_trunc(c[i]);
+        lo[i] = c[i] - hi[i];
       }
+      *p0 = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      *p1 = make_float4(lo[4], lo[5], lo[6], lo[7]);
       tmem_st8(tmem + tlane + k0, hi);
     }
     tmem_st_wait();
@@ -319,6 +382,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   __syncthreads();
   tc_fence_after();
 
+  if (tid == 0) tc_stamp(p, 0, 21);
   if (mma_warp) {
     // =====================================================================================================================
     // MMA / TMA warp: the whole warp runs the control flow and the waits, one elected lane issues
@@ -332,10 +396,25 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
     const uint64_t d_clo = umma_desc_k(smem_u32(Clo));
     // phase F of tile jj into its V buffer:  V_p += C_hi . A_hi ;  V_small += C_hi . A_lo + C_lo . A_hi
     // (inside the loops only the 14-bit start-address field of a descriptor moves, in units of 16 bytes)
+    // Pacing.  The tensor pipe's queue is a handful of MMAs deep; issue beyond that blocks, and a warp blocked there also holds
+    // up the TMEM loads / stores of the phase-Q warps of ITS scheduler (they arrived 1500-2000 cycles after the other six, and
+    // the pair moved with the MMA warp when it was put on another scheduler: profiles/round2_ncu_hera350.md section 7).
+    // Commit-based pacing costs ~500 cycles per round trip, so the issuing lane paces itself on the SM clock instead: it keeps
+    // an estimate of when the pipe will have finished what was issued (measured costs per MMA, tools/tc_probe.cu) and issues the
+    // next three MMAs only when less than PACE_SLACK cycles of work are left -- the queue stays about four deep and never blocks.
+    constexpr int PACE_SLACK = 45;  // issue the next group of three when about one MMA of work is left
+    const int cost_ts32 = 22, cost_ss32 = 41, cost_b = kpt / 2 + 2;
+    long long t_pipe = 0;
+    auto pace = [&](int cost) {
+      if (!use_pace) return;
+      long long now = clock64();
+      while (t_pipe - now > PACE_SLACK) now = clock64();
+      t_pipe = (t_pipe > now ? t_pipe : now) + cost;
+    };
     auto issue_f = [&](int jj) {
       const int sg = slot_of(jj, n_mn);
       const uint32_t vcol = tmem + L.col_v + L.v_stride * slot_of(jj, nbuf);
-      tc_wait(&bar_full[sg], par_of(jj, n_mn), p.dbg, 1, jj);
+      tc_wait(&bar_full[sg], par_of(jj, n_mn), p.dbg, 1, jj, l0);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sbase = mn_addr + sg * half_bytes;
@@ -343,6 +422,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
         uint32_t a_hi = tmem, vp = vcol;
         int in_part = 0;
         for (int ks = 0; ks < nks; ++ks) {
+          pace(2 * cost_ts32 + cost_ss32);
           umma_ts(vp, a_hi, b_hi, idesc_f, in_part ? 1u : 0u);
           umma_ts(vcol + L.v_small, a_hi, b_lo, idesc_f, ks ? 1u : 0u);
           umma_ss(vcol + L.v_small, a_lo, b_hi, idesc_f, 1u);
@@ -359,25 +439,11 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       }
       __syncwarp();
     };
-    issue_f(0);
-    for (int j = 0; j < ntiles; ++j) {
+    // phase B of tile j once phase Q has written dL/dv: dC += Q_hi . A_hi^T + Q_hi . A_lo^T + Q_lo . A_hi^T
+    auto issue_b = [&](int j) {
       const int sk = slot_of(j, n_k), vb = slot_of(j, nbuf);
-      tc_stamp(p, j, 0);
-      // two V buffers: phase F of the next tile runs on the tensor cores while phase Q of this one runs on the CUDA cores
-      if (nbuf == 2 && j + 1 < ntiles) issue_f(j + 1);
-      tc_stamp(p, j, 1);
-      if (j + n_mn < ntiles) {  // phase F of tile j has retired: its MN-major pair takes tile j + n_mn
-        tc_wait(&bar_v[vb], par_of(j, nbuf), p.dbg, 6, j);
-        if (elect_one()) {
-          const int sg = slot_of(j, n_mn);
-          mbar_expect_tx(&bar_full[sg], half_bytes);
-          bulk_g2s(smem + sg * half_bytes, Abase + (size_t)(j + n_mn) * tile_floats, half_bytes, &bar_full[sg]);
-        }
-        __syncwarp();
-      }
-      // ---- phase B once phase Q has written dL/dv: dC += Q_hi . A_hi^T + Q_hi . A_lo^T + Q_lo . A_hi^T
-      tc_wait(&bar_q[vb], par_of(j, nbuf), p.dbg, 2, j);
-      tc_wait(&bar_fullb[sk], par_of(j, n_k), p.dbg, 7, j);
+      tc_wait(&bar_q[vb], par_of(j, nbuf), p.dbg, 2, j, l0);
+      tc_wait(&bar_fullb[sk], par_of(j, n_k), p.dbg, 7, j, l0);
       tc_fence_after();
       tc_stamp(p, j, 2);
       if (elect_one()) {
@@ -387,6 +453,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t b_hi = d_b_hi + 2 * ks, b_lo = d_b_lo + 2 * ks;  // 32 B along the 128 B row
+          pace(3 * cost_b);
           umma_ts(tmem + L.col_dc, qhi + 8 * ks, b_hi, idesc_b, ks ? 1u : dc_accum);
           umma_ts(tmem + L.col_dc, qhi + 8 * ks, b_lo, idesc_b, 1u);
           umma_ts(tmem + L.col_dc, qlo + 8 * ks, b_hi, idesc_b, 1u);
@@ -399,17 +466,55 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       __syncwarp();
       dc_accum = 1u;
       tc_stamp(p, j, 3);
+    };
+    issue_f(0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int vb = slot_of(j, nbuf);
+      bool b_issued = false;
+      tc_stamp(p, j, 0);
+      if (nbuf == 2 && j + 1 < ntiles) {
+        // Two V buffers: phase F of the next tile runs on the tensor cores while phase Q of this one runs on the CUDA cores.
+        // If phase Q is already through (it is the shorter one for large classes), phase B goes first: the pipe then has
+        // phase F behind it, instead of idling between the two.
+        uint32_t ready;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ready) : "r"(smem_u32(&bar_q[vb])), "r"(par_of(j, nbuf)) : "memory");
+        if (b_first && __all_sync(0xffffffffu, ready != 0u)) {
+          issue_b(j);
+          b_issued = true;
+        }
+        issue_f(j + 1);
+      }
+      tc_stamp(p, j, 1);
+      if (!b_issued) issue_b(j);
       // one V buffer: the next phase F goes behind this phase B in the tensor pipe (its operands landed during phase Q)
       if (nbuf == 1 && j + 1 < ntiles) issue_f(j + 1);
-      if (j + n_k < ntiles) {  // the K-major pair is free once phase B has retired
-        tc_wait(&bar_free[sk], par_of(j, n_k), p.dbg, 3, j);
+      tc_stamp(p, j, 4);
+    }
+  } else if (tma_warp) {
+    // =====================================================================================================================
+    // TMA warp: refills the two tile rings as their stages retire -- off the MMA warp's path, whose issue is synchronous with the
+    // tensor pipe (a bulk copy or a wait there is a bubble in the pipe: measured, profiles/round2_ncu_hera350.md section 7)
+    // =====================================================================================================================
+    for (int j = 0; j < ntiles; ++j) {
+      if (j + n_mn < ntiles) {  // phase F of tile j has retired: its MN-major pair takes tile j + n_mn
+        tc_wait(&bar_v[slot_of(j, nbuf)], par_of(j, nbuf), p.dbg, 6, j, l0);
+        if (elect_one()) {
+          const int sg = slot_of(j, n_mn);
+          mbar_expect_tx(&bar_full[sg], half_bytes);
+          bulk_g2s(smem + sg * half_bytes, Abase + (size_t)(j + n_mn) * tile_floats, half_bytes, &bar_full[sg]);
+        }
+        __syncwarp();
+      }
+      if (j + n_k < ntiles) {   // phase B of tile j has retired: its K-major pair takes tile j + n_k
+        const int sk = slot_of(j, n_k);
+        tc_wait(&bar_free[sk], par_of(j, n_k), p.dbg, 3, j, l0);
         if (elect_one()) {
           mbar_expect_tx(&bar_fullb[sk], half_bytes);
           bulk_g2s(smem + L.off_k + sk * half_bytes, Abase + (size_t)(j + n_k) * tile_floats + 2 * kpt * 32, half_bytes, &bar_fullb[sk]);
         }
         __syncwarp();
       }
-      tc_stamp(p, j, 4);
     }
   } else {
     // =====================================================================================================================
@@ -421,37 +526,44 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
     const ClassSlot cs = s_cs[s];
     const int2 an = s_ant[s];
     float loss_acc = 0.f;
-    // this thread's inputs are loaded ONE TILE AHEAD (registers): their DRAM / L2 latency hides behind the previous tile's work
-    float4 in[7][2], nx[7][2];
-    auto load_inputs = [&](int jt, float4 (&dst)[7][2]) {
+    // this thread's inputs are loaded ONE TILE AHEAD (registers): their DRAM / L2 latency hides behind the previous tile's work.
+    // Two register sets, the tile loop unrolled by two (no copies).
+    f32x8 bufA[7], bufB[7];
+    auto load_inputs = [&](int jt, f32x8 (&dst)[7]) {
       const int f0 = (mt.j0 + jt) * C::FT + mycol;
       const int o = cs.bl0 * p.nfp + f0, o0 = an.x + f0, o1 = an.y + f0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        dst[0][h] = *reinterpret_cast<const float4*>(p.d_r + o + 4 * h);
-        dst[1][h] = *reinterpret_cast<const float4*>(p.d_i + o + 4 * h);
-        dst[2][h] = *reinterpret_cast<const float4*>(p.w + o + 4 * h);
-        dst[3][h] = *reinterpret_cast<const float4*>(g_r + o0 + 4 * h);
-        dst[4][h] = *reinterpret_cast<const float4*>(g_i + o0 + 4 * h);
-        dst[5][h] = *reinterpret_cast<const float4*>(g_r + o1 + 4 * h);
-        dst[6][h] = *reinterpret_cast<const float4*>(g_i + o1 + 4 * h);
+      dst[0] = ldg256(p.d_r + o);
+      dst[1] = ldg256(p.d_i + o);
+      dst[2] = ldg256(p.w + o);
+      dst[3] = ldg256(g_r + o0);
+      dst[4] = ldg256(g_i + o0);
+      dst[5] = ldg256(g_r + o1);
+      dst[6] = ldg256(g_i + o1);
+    };
+    // The per-baseline rows arrive 128 bytes per tile and row: every PF tiles each thread asks L2 for one line (group tid / 4, tile
+    // tid % 4 of the next PF tiles) of each of the three arrays, 2 PF tiles ahead -- neighbouring lanes walk along a row, so DRAM
+    // sees 512-byte pieces, and the loads below find L2.  (prefetch.global.L2 is an ordinary LSU instruction; the bulk-copy
+    // prefetch went through the TMA queue and delayed the tile copies behind 192 small requests.)
+    constexpr int PF = 4;
+    auto prefetch_rows = [&](int jt) {
+      const int ps = tid >> 2, pt = jt + (tid & 3);
+      if (use_prefetch && ps < nslots && pt < ntiles) {
+        const size_t o = (size_t)s_cs[ps].bl0 * p.nfp + (size_t)(mt.j0 + pt) * C::FT;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_r + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_i + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.w + o));
       }
     };
-    if (valid) load_inputs(0, nx);
-    for (int j = 0; j < ntiles; ++j) {
+    prefetch_rows(0);
+    prefetch_rows(PF);
+    auto do_tile = [&](int j, f32x8 (&in)[7], f32x8 (&nx)[7]) {
       const int f0 = (mt.j0 + j) * C::FT + mycol;
       const int vb = slot_of(j, nbuf);
-      if (valid) {
-#pragma unroll
-        for (int a = 0; a < 7; ++a) {
-          in[a][0] = nx[a][0];
-          in[a][1] = nx[a][1];
-        }
-        if (j + 1 < ntiles) load_inputs(j + 1, nx);
-      }
+      if ((j & (PF - 1)) == 0) prefetch_rows(j + 2 * PF);
+      if (valid && j + 1 < ntiles) load_inputs(j + 1, nx);
       const uint32_t vcol = tmem + tlane + L.col_v + L.v_stride * vb + cbase;
       if (tid == 0) tc_stamp(p, j, 6);
-      tc_wait(&bar_v[vb], par_of(j, nbuf), p.dbg, 4, j);
+      tc_wait(&bar_v[vb], par_of(j, nbuf), p.dbg, 4, j, l0);
       tc_fence_after();
       if (tid == 0) tc_stamp(p, j, 7);
       // V row of this thread, 16 columns: partial accumulators + the small terms, added with round-to-nearest
@@ -479,13 +591,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
 #pragma unroll
       for (int i = 0; i < 8; ++i) qr[i] = qi[i] = 0.f;
       if (valid) {
-        const float* dr = reinterpret_cast<const float*>(&in[0][0]);
-        const float* di = reinterpret_cast<const float*>(&in[1][0]);
-        const float* ww = reinterpret_cast<const float*>(&in[2][0]);
-        const float* gr0 = reinterpret_cast<const float*>(&in[3][0]);
-        const float* gi0 = reinterpret_cast<const float*>(&in[4][0]);
-        const float* gr1 = reinterpret_cast<const float*>(&in[5][0]);
-        const float* gi1 = reinterpret_cast<const float*>(&in[6][0]);
+        const float *dr = in[0].v, *di = in[1].v, *ww = in[2].v, *gr0 = in[3].v, *gi0 = in[4].v, *gr1 = in[5].v, *gi1 = in[6].v;
         float2 zz[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {  // calibration.py:1593-1609, as in the other kernels
@@ -500,9 +606,9 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
           qr[i] = P * er - Q * ei;
           qi[i] = Q * er + P * ei;
         }
-        float4* zdst = reinterpret_cast<float4*>(p.z + (size_t)(cs.bl0 * p.nfp + f0));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) zdst[i] = make_float4(zz[2 * i].x, zz[2 * i].y, zz[2 * i + 1].x, zz[2 * i + 1].y);
+        float* zdst = reinterpret_cast<float*>(p.z + (size_t)(cs.bl0 * p.nfp + f0));
+        stg256(zdst, zz[0].x, zz[0].y, zz[1].x, zz[1].y, zz[2].x, zz[2].y, zz[3].x, zz[3].y);
+        stg256(zdst + 8, zz[4].x, zz[4].y, zz[5].x, zz[5].y, zz[6].x, zz[6].y, zz[7].x, zz[7].y);
       }
       if (tid == 0) tc_stamp(p, j, 9);
       // back to rows: lane 2g needs q_r of all 16 columns, lane 2g + 1 q_i
@@ -523,23 +629,34 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       tmem_st16(tmem + tlane + L.col_qlo + 32 * vb + cbase, lo);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive_plain(&bar_q[vb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_plain(&bar_q[vb]);
       if (tid == 0) tc_stamp(p, j, 10);
+      tc_stamp(p, j, 12 + warp);
+    };
+    if (valid) load_inputs(0, bufA);
+    for (int j = 0; j < ntiles; j += 2) {
+      do_tile(j, bufA, bufB);
+      if (j + 1 < ntiles) do_tile(j + 1, bufB, bufA);
     }
     // ---- backward sums: wait for the last phase B, then row m of dC -> dcpart
     {
       const int last = ntiles - 1;
-      tc_wait(bar_done, 0, p.dbg, 5, last);
+      tc_wait(bar_done, 0, p.dbg, 5, last, l0);
       tc_fence_after();
-      float* dst = p.dcpart + (size_t)mt.seg * p.dc_plane + (size_t)cs.row0 * 2 + part;
+      // rows of dcpart are (re, im) pairs: lane 2g (re) takes the even vectors of both parts, lane 2g + 1 the odd ones
+      float2* dst = reinterpret_cast<float2*>(p.dcpart + (size_t)mt.seg * p.dc_plane) + cs.row0;
       const int k_lo = half * (kpt / 2), k_hi = k_lo + kpt / 2;
       for (int k0 = k_lo; k0 < k_hi; k0 += 8) {
         float d8[8];
         tmem_ld8(tmem + tlane + L.col_dc + k0, d8);  // .sync.aligned: the whole warp, also the lanes of missing groups
-        if (valid) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (k0 + i < mt.ncomp) dst[(size_t)(k0 + i) * 2] = d8[i];
+        for (int i = 0; i < 8; i += 2) {
+          // this lane keeps vector i + part: it sends the other one and receives the partner's value of its own
+          const float keep = part ? d8[i + 1] : d8[i], send = part ? d8[i] : d8[i + 1];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          const int k = k0 + i + part;
+          if (valid && k < mt.ncomp) dst[k] = part ? make_float2(recv, keep) : make_float2(keep, recv);
         }
       }
     }
@@ -550,6 +667,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
+    tc_stamp(p, 0, 22);
     double a = 0.0;
     for (int w8 = 0; w8 < 8; ++w8) a += (double)red[w8];
     double* dst = p.partials + (size_t)blockIdx.x * 4;

@@ -166,7 +166,7 @@ int calb2_debug_check_guards(int64_t* nbuffers, int64_t* nviolations);
  * another thread is blocked in a CUDA call). */
 int calb2_debug_tc_record(uint32_t* out16);
 /* Development aid: with CALB2_TC_PROF=<cta> set at plan creation, the SM-clock stamps of that CTA of the last tensor-core
- * launch, [32 tiles][12 slots] (slots: calfit_tc.cuh, tc_stamp). */
+ * launch, [32 tiles][24 slots] (slots: calfit_tc.cuh, tc_stamp). */
 int calb2_debug_tc_profile(calb2_plan* plan, int64_t* out, int32_t n);
 
 /* Once per calibrate_and_model_tensor call: mirrors calibration.py:1143-1152. */
