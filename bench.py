@@ -233,6 +233,15 @@ def pinned(a):
     return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 
 
+def measured_bf16_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        return float(m["bf16_tflops"]), "measured dense bf16, MEASURED_PEAKS.json (burst)"
+    except Exception:
+        return 2250.0, "nominal dense bf16 (MEASURED_PEAKS.json absent)"
+
+
 def fma_peak_tflops(clocks):
     import torch
 
@@ -378,10 +387,11 @@ def bench_single_integration(args, rank, world, local_rank, dist):
         esz = 8 if args.precision == 64 else 4
         heavy_bytes = esz * sh["n_a_nz"] + 3 * esz * sh["n_d"] + 2 * esz * sh["n_c_nz"]
         shared_path = info["n_class_slots"] > 0
+        tc_path = shared_path and info.get("n_tc_ctas", 0) > 0 and args.reg != "sum"
         traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu capture
             with open(os.path.join(ROOT, "profiles", "heavy_traffic.json")) as f:
-                tr = json.load(f).get(args.workload + ("_shared" if shared_path else ""))
+                tr = json.load(f).get(args.workload + ("_tc" if tc_path else "_shared" if shared_path else ""))
             if tr and world == 1 and args.reg != "sum":
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         except Exception:
@@ -389,7 +399,8 @@ def bench_single_integration(args, rank, world, local_rank, dist):
         heavy_avg_ms = heavy_ms / args.steps
         achieved = heavy_bytes / (heavy_avg_ms * 1e-3) / 1e9 if heavy_avg_ms > 0 else None
         iter_gbs = sizes["b_iter"] / (loop_ms / args.steps * 1e-3) / 1e9 / world
-        kernel = (f"shared_kernel<256|512,NQ={4 if args.reg == 'sum' else 2}> (two shapes, one basis pass)" if shared_path
+        kernel = ("shared_tc_kernel (tcgen05.mma kind::tf32, 3-term split; basis pass = this kernel + the streaming kernel's few items)"
+                  if tc_path else f"shared_kernel<256|512,NQ={4 if args.reg == 'sum' else 2}> (two shapes, one basis pass)" if shared_path
                   else ("generic forward + backward kernels (float64, two passes over the basis)" if info["generic"]
                         else f"heavy_kernel<FL={info['tile_freqs'] // 4},SUM={int(args.reg == 'sum')}>"))
         line = {
@@ -411,11 +422,15 @@ def bench_single_integration(args, rank, world, local_rank, dist):
                 "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": heavy_bytes,
                 "avg_launch_ms": heavy_avg_ms, "kernel_share_of_step": heavy_ms / loop_ms if loop_ms > 0 else None,
                 "iteration": {"b_iter_bytes": sizes["b_iter"], "per_gpu_gbs": iter_gbs, "frac": iter_gbs / peak},
+                "dram": ({"bytes_per_launch": traffic, "gbs": traffic / (heavy_avg_ms * 1e-3) / 1e9,
+                          "frac": traffic / (heavy_avg_ms * 1e-3) / 1e9 / peak,
+                          "what": "the bytes the kernel really moves (ncu, per launch) over the live launch duration"}
+                         if traffic and heavy_avg_ms > 0 else None),
                 "note": ("ALGORITHMIC bytes are SURVEY.md section 8(d)'s: every group's own basis rows counted once per "
-                         "iteration.  The shared-basis kernel does not move them: it keeps each DISTINCT basis once "
-                         "(L2-resident) and reads only the per-baseline arrays from DRAM (`traffic`), so achieved / "
-                         "peak exceeds 1; the kernel is bound by the FP32 FMA pipe, see roofline_fma.  The HBM-streaming "
-                         "kernel of round 1 is re-measured under `streaming`.") if shared_path else None,
+                         "iteration.  The shared-basis kernels do not move them: each DISTINCT basis is kept once "
+                         "(L2-resident) and only the per-baseline arrays come from DRAM (`traffic`, `dram`), so achieved / "
+                         "peak exceeds 1; what bounds the kernel is under `roofline_fma` (tensor pipe / FP32 FMA pipe).  The "
+                         "HBM-streaming kernel of round 1 is re-measured under `streaming`.") if shared_path else None,
             },
             "wall_ms_timed_call": wall_ms, "setup_s": setup_s,
             "setup_breakdown_s": {"synthesis": synth_s, "plan_create_and_basis_upload": plan_s,
@@ -424,12 +439,24 @@ def bench_single_integration(args, rank, world, local_rank, dist):
             "plan": {k: int(v) for k, v in info.items()},
         }
         if shared_path:
-            fpeak, fsrc = fma_peak_tflops(clocks)
             tf = 2.0 * info["class_fma"] / (heavy_avg_ms * 1e-3) / 1e12
-            line["roofline_fma"] = {"bound": "fp32_fma", "kernel": kernel, "achieved": tf, "peak": fpeak, "unit": "TFLOP/s",
-                                    "frac": tf / fpeak, "peak_source": fsrc, "flops_per_launch": 2 * info["class_fma"],
-                                    "what": "8 flops per (group, basis row, channel): forward + backward contraction, real + "
-                                            "imaginary part (SURVEY.md section 8d: 8 N_A_nz), over the basis-pass duration"}
+            if tc_path:
+                bf16, bsrc = measured_bf16_peak()
+                fpeak, fsrc = bf16 / 2.0, f"tf32 dense = half of the bf16 figure ({bsrc})"
+                line["roofline_fma"] = {
+                    "bound": "tensor", "kernel": kernel, "achieved": tf, "peak": fpeak, "unit": "TFLOP/s", "frac": tf / fpeak,
+                    "peak_source": fsrc, "flops_per_launch": 2 * info["class_fma"], "executed_over_algorithmic": 3.0,
+                    "what": "ALGORITHMIC flops (8 per group, basis row and channel: forward + backward contraction, real + "
+                            "imaginary part; SURVEY.md section 8d: 8 N_A_nz) over the basis-pass duration.  The tensor cores "
+                            "execute three TF32 MMAs per product (hi.hi + hi.lo + lo.hi) on 128-row tiles padded to 16 "
+                            "vectors, so the pipe does >= 3x this; the pass is bound by the CUDA-core phase between the two "
+                            "contractions and the MMA issue path, see profiles/round2_ncu_hera350.md section 7"}
+            else:
+                fpeak, fsrc = fma_peak_tflops(clocks)
+                line["roofline_fma"] = {"bound": "fp32_fma", "kernel": kernel, "achieved": tf, "peak": fpeak, "unit": "TFLOP/s",
+                                        "frac": tf / fpeak, "peak_source": fsrc, "flops_per_launch": 2 * info["class_fma"],
+                                        "what": "8 flops per (group, basis row, channel): forward + backward contraction, real + "
+                                                "imaginary part (SURVEY.md section 8d: 8 N_A_nz), over the basis-pass duration"}
         line["other_regularization"] = {
             "model_regularization": other, "value": args.steps / (loop_o_ms * 1e-3), "unit": UNIT,
             "ms_per_step": loop_o_ms / args.steps, "basis_pass_ms": heavy_o_ms / args.steps,

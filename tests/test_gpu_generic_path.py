@@ -97,17 +97,24 @@ def test_float64_loop_semantics_and_setup_stage(native_built):
     plan.close()
 
 
-def test_generic_float32_matches_fused_kernels(native_built, monkeypatch):
-    """CALB2_GENERIC=1 routes an ordinary float32 problem through the generic path: same trajectory as the fused kernels."""
+@pytest.mark.parametrize("tc", [False, True], ids=["cuda-cores", "tensor-cores"])
+def test_generic_float32_matches_fused_kernels(native_built, monkeypatch, tc):
+    """CALB2_GENERIC=1 routes an ordinary float32 problem through the generic path: same trajectory as the fused kernels.
+    Two float32 CUDA-core evaluations agree to 1e-5 in the parameters; the tensor-core shape (3-term TF32 split, truncating
+    accumulator: gradients within ~5e-6 of float64) is held to the north-star bound of 1e-4."""
     from calamity_b200.fitter import FitPlan
 
     prob = small_problem("hera37", init_gain_scatter=0.02, coeff_error=0.05)
     kw = dict(optimizer="Adamax", maxsteps=40, tol=0.0, learning_rate=1e-2)
+    monkeypatch.setenv("CALB2_TC", "1" if tc else "0")
+    monkeypatch.setenv("CALB2_TC_MIN", "1")
     outs = []
     for generic in (0, 1):
         monkeypatch.setenv("CALB2_GENERIC", str(generic))
         plan = FitPlan(prob.layout(), device=0)
         assert plan.info["generic"] == generic
+        if not generic:
+            assert (plan.info["n_tc_ctas"] > 0) == tc
         plan.set_integration(prob.data_r, prob.data_i, prob.wgts)
         plan.set_gains(prob.g0_r, prob.g0_i)
         plan.set_coeffs(prob.c0_r, prob.c0_i)
@@ -115,42 +122,5 @@ def test_generic_float32_matches_fused_kernels(native_built, monkeypatch):
         outs.append((hist, plan.get_gains()[0], plan.get_coeffs()[0]))
         plan.close()
     np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=2e-6)
-    assert rel_err(outs[1][1], outs[0][1]) < 1e-5 and rel_err(outs[1][2], outs[0][2]) < 1e-5
-
-
-def test_oversized_group_takes_the_generic_path(native_built):
-    """A fitting group with more basis vectors than the fused kernel stages (704) no longer fails: float32, generic path,
-    loss and gradient against the float64 oracle at BASELINE.json's tolerances."""
-    from calamity_b200.fitter import FitPlan
-    from calamity_b200.layout import RaggedLayout
-
-    rng = np.random.default_rng(11)
-    nants, nf, ncomp = 3, 1024, 800
-    basis, _ = np.linalg.qr(rng.standard_normal((nf, ncomp)))  # [nf, ncomp] orthonormal columns
-    small, _ = np.linalg.qr(rng.standard_normal((nf, 12)))
-    comps = [np.zeros((ncomp, 1, 1, nf)), np.zeros((12, 2, 1, nf))]
-    comps[0][:, 0, 0] = basis.T
-    comps[1][:, 0, 0] = small.T
-    comps[1][:, 1, 0] = small.T
-    corr = [[[(0, 1)]], [[(0, 2)], [(1, 2)]]]
-    fg_r = [rng.standard_normal((ncomp, 1, 1, 1)) * 0.05, rng.standard_normal((12, 2, 1, 1))]
-    fg_i = [rng.standard_normal((ncomp, 1, 1, 1)) * 0.05, rng.standard_normal((12, 2, 1, 1))]
-    g_r = 1.0 + 0.05 * rng.standard_normal((nants, nf))
-    g_i = 0.05 * rng.standard_normal((nants, nf))
-    data_r = [rng.standard_normal((1, 1, nf)), rng.standard_normal((2, 1, nf))]
-    data_i = [rng.standard_normal((1, 1, nf)), rng.standard_normal((2, 1, nf))]
-    wgts = [np.full((1, 1, nf), 1.0 / (3 * nf)), np.full((2, 1, nf), 1.0 / (3 * nf))]
-    ol, ogr, ogi, ofr, ofi = R.loss_and_grads(g_r, g_i, fg_r, fg_i, data_r, data_i, wgts, comps, corr)
-    lay = RaggedLayout.from_dense(comps, corr, nants)
-    plan = FitPlan(lay, device=0)
-    assert plan.info["generic"] == 1 and plan.info["dtype"] == 0
-    plan.set_integration(lay.flatten_data(data_r), lay.flatten_data(data_i), lay.flatten_data(wgts))
-    plan.set_gains(g_r, g_i)
-    plan.set_coeffs(lay.flatten_coeffs(fg_r), lay.flatten_coeffs(fg_i))
-    loss, dgr, dgi, dcr, dci = plan.loss_and_grads()
-    hist, res = plan.fit(optimizer="Adamax", maxsteps=5, tol=0.0, learning_rate=1e-3)
-    plan.close()
-    assert abs(float(loss) - float(ol)) <= 1e-5 * abs(float(ol)), (loss, ol)
-    assert rel_err(dgr, ogr) < 1e-4 and rel_err(dgi, ogi) < 1e-4
-    assert rel_err(dcr, lay.flatten_coeffs(ofr)) < 1e-4 and rel_err(dci, lay.flatten_coeffs(ofi)) < 1e-4
-    assert len(hist) == 5 and np.all(np.isfinite(hist)) and hist[-1] < hist[0]
+    ptol = 1e-4 if tc else 1e-5
+    assert rel_err(outs[1][1], outs[0][1]) < ptol and rel_err(outs[1][2], outs[0][2]) < ptol

@@ -148,7 +148,7 @@ def test_lamb_trust_ratio_is_per_chunk_variable(native_built, kw):
     groups of different sizes) must follow the float64 restatement run on the same per-chunk variables -- and must NOT
     follow the one that treats all coefficients as a single variable."""
     from calamity_b200.fitter import FitPlan
-    from helpers import mixed_problem
+    from tests.helpers import mixed_problem
     from oracle.ragged import RaggedProblem
 
     p = mixed_problem(nants=24, nfreqs=96, seed=3, n_dpss_bls=120, joint=((3, 9, 20), (2, 7, 12)))
