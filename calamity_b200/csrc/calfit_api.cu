@@ -5,6 +5,8 @@
 #include <nvtx3/nvToolsExt.h>  // header-only: the ranges cost nothing unless a profiler injects itself
 
 #include <algorithm>
+#include <functional>
+#include <queue>
 #include <climits>
 #include <cstdarg>
 #include <cmath>
@@ -196,6 +198,8 @@ struct calb2_plan {
   DevBuf<long long> tc_prof;          // CALB2_TC_PROF=<cta>: clock stamps of one CTA of the tensor-core kernel
   int tc_prof_cta = -1;
   int nseg[2] = {1, 1};               // channel segments per class tile = planes of dcpart in use
+  int nseg_tc = 1;                    // the same for the tensor-core tiles (chosen by a makespan model, below)
+  int dc_mode = -1;                   // which pass wrote dcpart last (planes a pass does not write must be zero)
   long long dc_plane = 0;             // floats per plane of dcpart
   int first_class_row = 0;            // rows below it belong to the streaming path (plane 0 only)
   DevBuf<ClassSlot> d_cslots;
@@ -513,6 +517,13 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
   if (fork_large || fork_items) return cudaStreamWaitEvent(s, pl->ev_join, 0);
   return cudaSuccess;
 }
+// A pass writes, for every class row, the planes of ITS segmentation only; coeffs_kernel adds nplanes of them.  Before the first
+// pass of another kind (CUDA-core plain / 'sum' / tensor-core) the whole buffer is cleared, so planes a class does not write are 0.
+static cudaError_t prepare_dcpart(calb2_plan* pl, int mode) {
+  if (pl->dc_mode == mode || pl->classes.empty()) return cudaSuccess;
+  pl->dc_mode = mode;
+  return cudaMemsetAsync(pl->dcpart.p, 0, pl->dcpart.bytes(), pl->stream);
+}
 // partial-sum slots of one pass; with the tensor-core shape in use the layout is items | small rest | large | tensor-core
 static int n_partials(const calb2_plan* pl, bool sum) {
   const int v = sum ? 1 : 0;
@@ -608,7 +619,9 @@ static GainsParams gains_params(calb2_plan* pl, const FitState* st, const FitCon
   return gp;
 }
 
-static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitConsts& k, int mode, bool sum) {
+// tc_pass: the backward sums come from a pass that used the tensor-core kernel (plain chi^2 fit / evaluation passes)
+static bool tc_pass_of(const calb2_plan* pl, bool sum) { return pl->tc_enabled && !sum && !pl->mt_tc.empty(); }
+static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitConsts& k, int mode, bool sum, bool tc_pass = false) {
   CoeffParams cp{};
   cp.dcpart = pl->dcpart.p;
   cp.coef_row0 = pl->coef_row0.p;
@@ -631,7 +644,7 @@ static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitCon
   cp.k = k;
   cp.ncoef = (int)pl->ncoef;
   cp.nq = sum ? 4 : 2;
-  cp.nplanes = pl->classes.empty() ? 1 : pl->nseg[sum ? 1 : 0];
+  cp.nplanes = pl->classes.empty() ? 1 : (tc_pass ? std::max(pl->nseg[0], pl->nseg_tc) : pl->nseg[sum ? 1 : 0]);
   cp.plane = pl->dc_plane;
   cp.first_class_row = pl->first_class_row;
   cp.mode = mode;
@@ -812,7 +825,7 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
     CU(cudaEventRecord(pl->ev_fork, pl->stream));
     CU(cudaStreamWaitEvent(pl->stream2, pl->ev_fork, 0));
     // mode 0: optimizer step from the stored backward sums; mode 3: only the use_min snapshot copy
-    coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream2>>>(coeff_params(pl, pl->state.p, k, fuse ? 3 : 0, sum));
+    coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream2>>>(coeff_params(pl, pl->state.p, k, fuse ? 3 : 0, sum, tc_pass_of(pl, sum)));
     CU(cudaGetLastError());
     CU(cudaEventRecord(pl->ev_join, pl->stream2));
     forked = true;
@@ -927,7 +940,7 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
       gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 5, sum, 0));
       CU(cudaGetLastError());
       if (!freeze) {
-        coeffs_kernel<<<cgrid, 256, 0, pl->stream>>>(coeff_params(pl, pl->state.p, k, 5, sum));
+        coeffs_kernel<<<cgrid, 256, 0, pl->stream>>>(coeff_params(pl, pl->state.p, k, 5, sum, tc_pass_of(pl, sum)));
         CU(cudaGetLastError());
         LambNormParams np{};
         np.c_r = pl->c_r.p;
@@ -953,7 +966,7 @@ static int enqueue_step(calb2_plan* pl, const FitConsts& k, bool sum, bool freez
       gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state.p, k, 6, sum, 0));
       CU(cudaGetLastError());
       if (!freeze) {
-        coeffs_kernel<<<cgrid, 256, 0, pl->stream>>>(coeff_params(pl, pl->state.p, k, 6, sum));
+        coeffs_kernel<<<cgrid, 256, 0, pl->stream>>>(coeff_params(pl, pl->state.p, k, 6, sum, tc_pass_of(pl, sum)));
         CU(cudaGetLastError());
       }
       *launches += freeze ? 1 : 4;
@@ -985,6 +998,7 @@ static int init_coeffs_impl(calb2_plan* pl, const float* sky_r, const float* sky
   HeavyParams hp = heavy_params(pl, pl->state_eval.p, false, 0, 1);
   hp.d_r = pl->sky_r.p;
   hp.d_i = pl->sky_i.p;
+  CU(prepare_dcpart(pl, 1));
   CU(launch_heavy(pl, false, hp, (int)pl->items.size(), pl->stream));
   FitConsts k{};
   coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(coeff_params(pl, pl->state_eval.p, k, 1, false));
@@ -1381,6 +1395,41 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     // planes of dcpart and are added, in order, by coeffs_kernel.
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device);
+    {
+      // Tensor-core tiles: one CTA per SM, ~12 000 cycles of prologue + epilogue per CTA, ~3000 cycles per 32-channel tile up to
+      // 160 vectors and ~6000 above (measured, profiles/round2_ncu_hera350.md section 7).  The number of channel segments is the
+      // candidate with the smallest makespan of a longest-first greedy schedule over the SMs -- at HERA-350 on one GPU that is
+      // 1 or 3 (1011 or 3033 CTAs), on an eighth of it 2-3 instead of the CUDA-core rule's 8.
+      auto tile_cost = [](int kpt) { return kpt <= 128 ? 3000.0 : (kpt <= 160 ? 3400.0 : 6000.0); };
+      double best = 1e300;
+      for (int cand : {1, 2, 3, 4, 6, 8}) {
+        if (cand > pl->ntiles_c) break;
+        std::vector<double> costs;
+        for (const auto& ci : pl->classes)
+          if (ci.tc)
+            for (int m0 = 0; m0 < ci.nmembers; m0 += TcCfg::MS)
+              for (int sg = 0; sg < cand; ++sg) {
+                const int nt = (int)((long long)pl->ntiles_c * (sg + 1) / cand) - (int)((long long)pl->ntiles_c * sg / cand);
+                costs.push_back(12000.0 + nt * tile_cost(ci.kpt));
+              }
+        if (costs.empty()) break;
+        std::sort(costs.begin(), costs.end(), std::greater<double>());
+        std::priority_queue<double, std::vector<double>, std::greater<double>> sms;
+        for (int i = 0; i < nsm; ++i) sms.push(0.0);
+        double makespan = 0.0;
+        for (double c : costs) {
+          const double t = sms.top() + c;
+          sms.pop();
+          sms.push(t);
+          makespan = std::max(makespan, t);
+        }
+        if (makespan < best * 0.98) {  // prefer fewer segments on a near tie
+          best = makespan;
+          pl->nseg_tc = cand;
+        }
+      }
+      if (getenv("CALB2_NSEG_TC")) pl->nseg_tc = std::max(1, std::min(pl->ntiles_c, atoi(getenv("CALB2_NSEG_TC"))));
+    }
     for (int v = 0; v < 2; ++v) {
       long long base = 0;
       for (const auto& ci : pl->classes) base += (ci.nmembers + shared_ms(v, ci.kp <= KPM_SMALL ? 0 : 1) - 1) / shared_ms(v, ci.kp <= KPM_SMALL ? 0 : 1);
@@ -1408,7 +1457,8 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
           }
         if (v == 0 && ci.tc)  // the same class as 64-group tiles of the tensor-core shape
           for (int m0 = 0; m0 < ci.nmembers; m0 += TcCfg::MS)
-            for (int sg = 0; sg < nseg; ++sg) {
+            for (int sg = 0; sg < pl->nseg_tc; ++sg) {
+              const int nseg = pl->nseg_tc;
               MTileDesc mt{};
               mt.a_off = ci.tc_off;
               mt.kp = ci.kpt;
@@ -1571,7 +1621,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(dalloc(pl->cm_i, (size_t)nc, pl));
   TRY(dalloc(pl->cu_i, (size_t)nc, pl));
   pl->dc_plane = rows * 4;
-  TRY(dalloc(pl->dcpart, (size_t)pl->dc_plane * std::max(pl->nseg[0], pl->nseg[1]), pl));
+  TRY(dalloc(pl->dcpart, (size_t)pl->dc_plane * std::max(std::max(pl->nseg[0], pl->nseg[1]), pl->nseg_tc), pl));
   TRY(dalloc(pl->partials, (size_t)n_partials_max(pl) * 4, pl));
   TRY(upload(pl->d_mt_tc, pl->mt_tc, pl));
   TRY(upload(pl->d_mt_small_rest, pl->mt_small_rest, pl));
@@ -1980,6 +2030,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, double prior_r,
   k.prior_r = (float)prior_r;
   k.prior_i = (float)prior_i;
   HeavyParams hp = heavy_params(pl, pl->state_eval.p, sum, 0, 0);
+  CU(prepare_dcpart(pl, tc_pass_of(pl, sum) ? 3 : (sum ? 2 : 1)));
   CU(launch_heavy(pl, sum, hp, (int)pl->items.size(), pl->stream));
   FinalizeParams fp{};
   fp.partials = pl->partials.p;
@@ -1996,7 +2047,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, double prior_r,
   dim3 ggrid(pl->nants, (pl->nfp + GK_CH - 1) / GK_CH);
   gains_kernel<<<ggrid, GK_THREADS, 0, pl->stream>>>(gains_params(pl, pl->state_eval.p, k, 1, sum, 1));
   CU(cudaGetLastError());
-  coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(coeff_params(pl, pl->state_eval.p, k, 1, sum));
+  coeffs_kernel<<<(unsigned)((pl->ncoef + 255) / 256), 256, 0, pl->stream>>>(coeff_params(pl, pl->state_eval.p, k, 1, sum, tc_pass_of(pl, sum)));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(pl->h_state, pl->state_eval.p, sizeof(FitState), cudaMemcpyDeviceToHost, pl->stream));
   CU(cudaStreamSynchronize(pl->stream));
@@ -2111,6 +2162,7 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
     pl->stage_cursor = 0;
   }
 #endif
+  if (!freeze) CU(prepare_dcpart(pl, tc_pass_of(pl, sum) ? 3 : (sum ? 2 : 1)));
   FitState s0{};
   s0.step = 0;
   s0.stop_after = (int)(total - 1);
