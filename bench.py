@@ -387,7 +387,7 @@ def bench_single_integration(args, rank, world, local_rank, dist):
         esz = 8 if args.precision == 64 else 4
         heavy_bytes = esz * sh["n_a_nz"] + 3 * esz * sh["n_d"] + 2 * esz * sh["n_c_nz"]
         shared_path = info["n_class_slots"] > 0
-        tc_path = shared_path and info.get("n_tc_ctas", 0) > 0 and args.reg != "sum"
+        tc_path = shared_path and info.get("n_tc_ctas", 0) > 0  # 'sum' too: two launches of the tensor-core kernel per pass
         traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu capture
             with open(os.path.join(ROOT, "profiles", "heavy_traffic.json")) as f:
@@ -399,7 +399,9 @@ def bench_single_integration(args, rank, world, local_rank, dist):
         heavy_avg_ms = heavy_ms / args.steps
         achieved = heavy_bytes / (heavy_avg_ms * 1e-3) / 1e9 if heavy_avg_ms > 0 else None
         iter_gbs = sizes["b_iter"] / (loop_ms / args.steps * 1e-3) / 1e9 / world
-        kernel = ("shared_tc_kernel (tcgen05.mma kind::tf32, 3-term split; basis pass = this kernel + the streaming kernel's few items)"
+        kernel = (("shared_tc_kernel<0> (tcgen05.mma kind::tf32, 3-term split; basis pass = this kernel + the streaming kernel's few items)"
+                   if args.reg != "sum" else "shared_tc_kernel<1> + <2> (tcgen05.mma kind::tf32, 3-term split; the second launch is the "
+                   "regulariser's backward rows)")
                   if tc_path else f"shared_kernel<256|512,NQ={4 if args.reg == 'sum' else 2}> (two shapes, one basis pass)" if shared_path
                   else ("generic forward + backward kernels (float64, two passes over the basis)" if info["generic"]
                         else f"heavy_kernel<FL={info['tile_freqs'] // 4},SUM={int(args.reg == 'sum')}>"))

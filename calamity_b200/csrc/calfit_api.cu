@@ -189,10 +189,11 @@ struct calb2_plan {
   DevBuf<MTileDesc> d_mtiles[2][2];
   // tensor-core shape: its CTAs (64 groups of a class of <= 128 vectors) and, when it is in use, the 256-thread CTAs of the
   // remaining small classes (129-160 vectors)
-  std::vector<MTileDesc> mt_tc, mt_small_rest, mt_large_rest;  // tensor-core tiles; the classes it does not take, per CUDA-core shape
-  DevBuf<MTileDesc> d_mt_tc, d_mt_small_rest, d_mt_large_rest;
+  std::vector<MTileDesc> mt_tc, mt_rest[2][2];  // tensor-core tiles; the classes it does not take, [plain / 'sum'][CUDA-core shape]
+  DevBuf<MTileDesc> d_mt_tc, d_mt_rest[2][2];
   DevBuf<float> At;
   bool tc_enabled = false;
+  bool tc_sum = true;                 // 'sum' on the tensor cores too (two launches); CALB2_TC_SUM=0: CUDA-core shapes
   size_t tc_smem_bytes = 0;           // dynamic shared memory of the tensor-core launch: the largest class's layout
   unsigned int* tc_dbg = nullptr;     // mapped host memory: record of a tensor-core wait that timed out
   DevBuf<long long> tc_prof;          // CALB2_TC_PROF=<cta>: clock stamps of one CTA of the tensor-core kernel
@@ -396,15 +397,18 @@ static int shared_ms(int v, int shape) { return (shape == 0 ? 64 : 128) / (v == 
 // The basis pass of one iteration: the streaming kernel over the items (groups with a private basis) and the
 // shared-basis kernel over the class tiles (its large-class shape on the second stream, next to the small-class one);
 // all of them write z / dcpart / partials for their own baselines and rows.
+static bool tc_pass_of(const calb2_plan* pl, bool sum);
 static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParams& hp, int nitems, cudaStream_t s) {
   const int v = sum ? 1 : 0;
-  // tensor-core shape: the fit's own passes (plain chi^2); initialisation / model-only passes and 'sum' stay on the CUDA cores
-  const bool use_tc = pl->tc_enabled && !sum && !hp.init_mode && !hp.store_v && !pl->mt_tc.empty();
+  // tensor-core shape: the fit's own passes; initialisation / model-only passes stay on the CUDA cores.  With the 'sum'
+  // regulariser the kernel runs twice: as for the plain chi^2 (plus y and the two model sums), then once more without phase F
+  // for the two extra backward rows (P w, Q w of calibration.py:1654: they depend on the gains and weights only).
+  const bool use_tc = tc_pass_of(pl, sum) && !hp.init_mode && !hp.store_v;
   const int n_tc = use_tc ? (int)pl->mt_tc.size() : 0;
-  const MTileDesc* small_tiles = use_tc ? pl->d_mt_small_rest.p : pl->d_mtiles[v][0].p;
-  const int n_small = use_tc ? (int)pl->mt_small_rest.size() : (int)pl->mtiles[v][0].size();
-  const MTileDesc* large_tiles = use_tc ? pl->d_mt_large_rest.p : pl->d_mtiles[v][1].p;
-  const int n_large = use_tc ? (int)pl->mt_large_rest.size() : (int)pl->mtiles[v][1].size();
+  const MTileDesc* small_tiles = use_tc ? pl->d_mt_rest[v][0].p : pl->d_mtiles[v][0].p;
+  const int n_small = use_tc ? (int)pl->mt_rest[v][0].size() : (int)pl->mtiles[v][0].size();
+  const MTileDesc* large_tiles = use_tc ? pl->d_mt_rest[v][1].p : pl->d_mtiles[v][1].p;
+  const int n_large = use_tc ? (int)pl->mt_rest[v][1].size() : (int)pl->mtiles[v][1].size();
   SharedParams sp{};
   if (n_small + n_large > 0) {
     sp.A = hp.A;
@@ -500,11 +504,23 @@ static cudaError_t launch_heavy(const calb2_plan* pl, bool sum, const HeavyParam
     static bool configured[MAX_DEVICES] = {};
     const int dev = current_device();
     if (!configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(shared_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(shared_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(shared_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(shared_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return e;
       configured[dev] = true;
     }
-    shared_tc_kernel<<<n_tc, TcCfg::NTHR, pl->tc_smem_bytes, s>>>(tp);
+    tp.y = hp.y;
+    tp.mode = sum ? 1 : 0;
+    if (sum) {  // the pass of the plain chi^2 plus y and the model sums, then the two extra backward rows of the regulariser
+      shared_tc_kernel<1><<<n_tc, TcCfg::NTHR, pl->tc_smem_bytes, s>>>(tp);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      tp.mode = 2;
+      shared_tc_kernel<2><<<n_tc, TcCfg::NTHR, pl->tc_smem_bytes, s>>>(tp);
+    } else {
+      shared_tc_kernel<0><<<n_tc, TcCfg::NTHR, pl->tc_smem_bytes, s>>>(tp);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -527,14 +543,15 @@ static cudaError_t prepare_dcpart(calb2_plan* pl, int mode) {
 // partial-sum slots of one pass; with the tensor-core shape in use the layout is items | small rest | large | tensor-core
 static int n_partials(const calb2_plan* pl, bool sum) {
   const int v = sum ? 1 : 0;
-  if (pl->tc_enabled && !sum && !pl->mt_tc.empty())
-    return (int)(pl->items.size() + pl->mt_small_rest.size() + pl->mt_large_rest.size() + pl->mt_tc.size());
+  if (tc_pass_of(pl, sum))
+    return (int)(pl->items.size() + pl->mt_rest[v][0].size() + pl->mt_rest[v][1].size() + pl->mt_tc.size());
   return (int)(pl->items.size() + pl->mtiles[v][0].size() + pl->mtiles[v][1].size());
 }
 static int n_partials_max(const calb2_plan* pl) {
   int n = 0;
   for (int v = 0; v < 2; ++v) n = std::max(n, (int)(pl->items.size() + pl->mtiles[v][0].size() + pl->mtiles[v][1].size()));
-  return std::max(n, (int)(pl->items.size() + pl->mt_small_rest.size() + pl->mt_large_rest.size() + pl->mt_tc.size()));
+  for (int v = 0; v < 2; ++v) n = std::max(n, (int)(pl->items.size() + pl->mt_rest[v][0].size() + pl->mt_rest[v][1].size() + pl->mt_tc.size()));
+  return n;
 }
 
 static HeavyParams heavy_params(calb2_plan* pl, const FitState* st, bool sum, int store_v, int init_mode) {
@@ -620,7 +637,7 @@ static GainsParams gains_params(calb2_plan* pl, const FitState* st, const FitCon
 }
 
 // tc_pass: the backward sums come from a pass that used the tensor-core kernel (plain chi^2 fit / evaluation passes)
-static bool tc_pass_of(const calb2_plan* pl, bool sum) { return pl->tc_enabled && !sum && !pl->mt_tc.empty(); }
+static bool tc_pass_of(const calb2_plan* pl, bool sum) { return pl->tc_enabled && (!sum || pl->tc_sum) && !pl->mt_tc.empty(); }
 static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitConsts& k, int mode, bool sum, bool tc_pass = false) {
   CoeffParams cp{};
   cp.dcpart = pl->dcpart.p;
@@ -644,7 +661,7 @@ static CoeffParams coeff_params(calb2_plan* pl, const FitState* st, const FitCon
   cp.k = k;
   cp.ncoef = (int)pl->ncoef;
   cp.nq = sum ? 4 : 2;
-  cp.nplanes = pl->classes.empty() ? 1 : (tc_pass ? std::max(pl->nseg[0], pl->nseg_tc) : pl->nseg[sum ? 1 : 0]);
+  cp.nplanes = pl->classes.empty() ? 1 : (tc_pass ? std::max(pl->nseg[sum ? 1 : 0], pl->nseg_tc) : pl->nseg[sum ? 1 : 0]);
   cp.plane = pl->dc_plane;
   cp.first_class_row = pl->first_class_row;
   cp.mode = mode;
@@ -1377,6 +1394,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     // a tensor-core CTA costs the same for 1 or 64 groups (128 accumulator rows): classes of up to 128 vectors with fewer than
     // tc_min members stay on the CUDA-core shapes (32 / 64 groups per CTA, cost by 8-group block).  Larger classes always go to
     // the tensor cores: a handful of them on the large CUDA-core shape took 435 us at HERA-350, next to a 650 us pass.
+    pl->tc_sum = !(getenv("CALB2_TC_SUM") && atoi(getenv("CALB2_TC_SUM")) == 0);
     int tc_min = 16;
     if (getenv("CALB2_TC_MIN")) tc_min = std::max(1, atoi(getenv("CALB2_TC_MIN")));
     long long tc_off = 0;
@@ -1453,7 +1471,7 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
             mt.j1 = (int)((long long)pl->ntiles_c * (sg + 1) / nseg);
             mt.seg = sg;
             pl->mtiles[v][shape].push_back(mt);
-            if (v == 0 && !ci.tc) (shape == 0 ? pl->mt_small_rest : pl->mt_large_rest).push_back(mt);
+            if (!ci.tc) pl->mt_rest[v][shape].push_back(mt);
           }
         if (v == 0 && ci.tc)  // the same class as 64-group tiles of the tensor-core shape
           for (int m0 = 0; m0 < ci.nmembers; m0 += TcCfg::MS)
@@ -1477,10 +1495,12 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
         const long long cb = (long long)(b.j1 - b.j0) * (b.kp + 40) * ((b.nslots + 7) / 8);
         return ca > cb;
       };
-      for (int shape = 0; shape < 2; ++shape) std::stable_sort(pl->mtiles[v][shape].begin(), pl->mtiles[v][shape].end(), by_cost);
+      for (int shape = 0; shape < 2; ++shape) {
+        std::stable_sort(pl->mtiles[v][shape].begin(), pl->mtiles[v][shape].end(), by_cost);
+        std::stable_sort(pl->mt_rest[v][shape].begin(), pl->mt_rest[v][shape].end(), by_cost);
+      }
       if (v == 0) {
-        std::stable_sort(pl->mt_small_rest.begin(), pl->mt_small_rest.end(), by_cost);
-        std::stable_sort(pl->mt_large_rest.begin(), pl->mt_large_rest.end(), by_cost);
+
         std::stable_sort(pl->mt_tc.begin(), pl->mt_tc.end(), by_cost);
       }
     }
@@ -1624,8 +1644,8 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
   TRY(dalloc(pl->dcpart, (size_t)pl->dc_plane * std::max(std::max(pl->nseg[0], pl->nseg[1]), pl->nseg_tc), pl));
   TRY(dalloc(pl->partials, (size_t)n_partials_max(pl) * 4, pl));
   TRY(upload(pl->d_mt_tc, pl->mt_tc, pl));
-  TRY(upload(pl->d_mt_small_rest, pl->mt_small_rest, pl));
-  TRY(upload(pl->d_mt_large_rest, pl->mt_large_rest, pl));
+  for (int v = 0; v < 2; ++v)
+    for (int shape = 0; shape < 2; ++shape) TRY(upload(pl->d_mt_rest[v][shape], pl->mt_rest[v][shape], pl));
   {
     long long tc_floats = 0;
     for (const auto& ci : pl->classes)
@@ -1692,8 +1712,8 @@ int calb2_plan_destroy(calb2_plan* pl) {
   for (int v = 0; v < 2; ++v)
     for (int shape = 0; shape < 2; ++shape) pl->d_mtiles[v][shape].release();
   pl->d_mt_tc.release();
-  pl->d_mt_small_rest.release();
-  pl->d_mt_large_rest.release();
+  for (int v = 0; v < 2; ++v)
+    for (int shape = 0; shape < 2; ++shape) pl->d_mt_rest[v][shape].release();
   pl->At.release();
   pl->d_cslots.release();
   pl->d_cs_slot.release();
@@ -2030,7 +2050,7 @@ int calb2_loss_and_grads(calb2_plan* pl, int32_t regularization, double prior_r,
   k.prior_r = (float)prior_r;
   k.prior_i = (float)prior_i;
   HeavyParams hp = heavy_params(pl, pl->state_eval.p, sum, 0, 0);
-  CU(prepare_dcpart(pl, tc_pass_of(pl, sum) ? 3 : (sum ? 2 : 1)));
+  CU(prepare_dcpart(pl, tc_pass_of(pl, sum) ? (sum ? 4 : 3) : (sum ? 2 : 1)));
   CU(launch_heavy(pl, sum, hp, (int)pl->items.size(), pl->stream));
   FinalizeParams fp{};
   fp.partials = pl->partials.p;
@@ -2162,7 +2182,7 @@ int calb2_fit(calb2_plan* pl, const calb2_fit_options* o, void* loss_history_v, 
     pl->stage_cursor = 0;
   }
 #endif
-  if (!freeze) CU(prepare_dcpart(pl, tc_pass_of(pl, sum) ? 3 : (sum ? 2 : 1)));
+  if (!freeze) CU(prepare_dcpart(pl, tc_pass_of(pl, sum) ? (sum ? 4 : 3) : (sum ? 2 : 1)));
   FitState s0{};
   s0.step = 0;
   s0.stop_after = (int)(total - 1);

@@ -231,6 +231,7 @@ struct TcParams {
   const float* c_r;
   const float* c_i;
   float2* z;
+  float2* y;            // 'sum' (mode 1): w v per visibility, read by the gain-gradient kernel
   float* dcpart;
   long long dc_plane;
   double* partials;
@@ -239,6 +240,8 @@ struct TcParams {
   unsigned int* dbg;    // mapped host memory: [0] = code of a wait that timed out, [1] tile, [2] CTA, [3] thread
   long long* prof;      // development aid (CALB2_TC_PROF=<cta>): clock64 stamps of that CTA, [tile][TC_PROF_SLOTS]
   int prof_cta;
+  int mode;             // (= the kernel's template argument) 0: plain chi^2 (two backward rows per group, dcpart rows of 2); 1: 'sum', first launch: the same plus y and
+                        // the model sums, dcpart rows of 4; 2: 'sum', second launch: no phase F, the backward rows P w / Q w
   int flags;            // development switches (CALB2_TC_FLAGS): 1 lane-0 polling, 2 L2 row prefetch, 4 clock-paced issue, 8 phase B first when ready
 };
 constexpr int TC_PROF_SLOTS = 24, TC_PROF_TILES = 32;  // 0-4 MMA warp, 6-10 phase-Q warp 0, 12-19 arrival of each phase-Q warp, 20-22 (tile 0) start / prologue / end
@@ -246,6 +249,7 @@ __device__ __forceinline__ void tc_stamp(const TcParams& p, int j, int slot) {
   if (p.prof && (int)blockIdx.x == p.prof_cta && j < TC_PROF_TILES && (threadIdx.x & 31) == 0) p.prof[j * TC_PROF_SLOTS + slot] = clock64();
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParams p) {
   using C = TcCfg;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -258,13 +262,16 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   const int kpt = mt.kp, nslots = mt.nslots;
   const TcLayout L = tc_layout(kpt);
   const bool l0 = p.flags & 1, use_prefetch = p.flags & 2, use_pace = p.flags & 4, b_first = p.flags & 8;
+  constexpr int mode = MODE;        // compile-time: the plain pass keeps its instruction stream and registers
+  constexpr bool no_f = MODE == 2;  // second launch of 'sum': backward contraction only
 
   float* Clo = reinterpret_cast<float*>(smem + L.off_clo);
   ClassSlot* s_cs = reinterpret_cast<ClassSlot*>(smem + L.off_cs);
   int2* s_ant = reinterpret_cast<int2*>(smem + L.off_ant);
   float* red = reinterpret_cast<float*>(smem + L.off_red);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-  uint64_t *bar_full = bars, *bar_fullb = bars + 2, *bar_free = bars + 4, *bar_v = bars + 6, *bar_q = bars + 8, *bar_done = bars + 10;
+  uint64_t *bar_full = bars, *bar_fullb = bars + 2, *bar_free = bars + 4, *bar_v = bars + 6, *bar_q = bars + 8, *bar_done = bars + 10,
+           *bar_b = bars + 12;  // mode 2 only: phase B of the tile in V buffer b retired -> phase Q may overwrite dL/dv there
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -293,8 +300,10 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       mbar_init(&bar_q[0], C::NEPI / 32);
       mbar_init(&bar_q[1], C::NEPI / 32);
       mbar_init(bar_done, 1);
+      mbar_init(&bar_b[0], 1);
+      mbar_init(&bar_b[1], 1);
       mbar_fence_init();
-      for (int jj = 0; jj < n_mn && jj < ntiles; ++jj) {
+      for (int jj = 0; jj < n_mn && jj < ntiles && !no_f; ++jj) {
         mbar_expect_tx(&bar_full[jj], half_bytes);
         bulk_g2s(smem + jj * half_bytes, Abase + jj * tile_floats, half_bytes, &bar_full[jj]);
       }
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
   const bool valid = q_warp && s < nslots;
 
   // ---- coefficients: hi part -> TMEM (the A-operand of phase F for the whole pass), lo part -> shared memory operand
-  if (q_warp) {
+  if (q_warp && !no_f) {
     // pass 1, coalesced: warp w brings rows 16 w .. 16 w + 15 (a group's coefficients are contiguous: lanes run over the vectors)
     // into the C lo buffer, already at their K-major SWIZZLE_128B positions (chunk of 32 vectors, row m, 16-byte pieces XOR-ed
     // with m & 7).  Lane-per-row loads cost 32 L1 wavefronts per instruction and made this prologue 17 000 cycles long.
@@ -459,6 +468,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
           umma_ts(tmem + L.col_dc, qlo + 8 * ks, b_hi, idesc_b, 1u);
         }
         umma_commit(&bar_free[sk]);
+        if (no_f) umma_commit(&bar_b[vb]);  // no phase F in between: phase Q of the next tile in this buffer waits for this instead
         // the accumulator is final after the last phase B.  (Its own barrier: with a one-entry ring the parity of free[] repeats
         // every two tiles, and a phase-Q warp can get here while phase B of the tile before the last is still in flight.)
         if (j == ntiles - 1) umma_commit(bar_done);
@@ -467,15 +477,14 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       dc_accum = 1u;
       tc_stamp(p, j, 3);
     };
-    issue_f(0);
+    if (!no_f) issue_f(0);
     for (int j = 0; j < ntiles; ++j) {
       const int vb = slot_of(j, nbuf);
       bool b_issued = false;
       tc_stamp(p, j, 0);
-      if (nbuf == 2 && j + 1 < ntiles) {
+      if (!no_f && nbuf == 2 && j + 1 < ntiles) {
         // Two V buffers: phase F of the next tile runs on the tensor cores while phase Q of this one runs on the CUDA cores.
-        // If phase Q is already through (it is the shorter one for large classes), phase B goes first: the pipe then has
-        // phase F behind it, instead of idling between the two.
+        // (switch 8: if phase Q is already through, phase B goes first)
         uint32_t ready;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ready) : "r"(smem_u32(&bar_q[vb])), "r"(par_of(j, nbuf)) : "memory");
@@ -488,7 +497,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       tc_stamp(p, j, 1);
       if (!b_issued) issue_b(j);
       // one V buffer: the next phase F goes behind this phase B in the tensor pipe (its operands landed during phase Q)
-      if (nbuf == 1 && j + 1 < ntiles) issue_f(j + 1);
+      if (!no_f && nbuf == 1 && j + 1 < ntiles) issue_f(j + 1);
       tc_stamp(p, j, 4);
     }
   } else if (tma_warp) {
@@ -497,7 +506,7 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
     // tensor pipe (a bulk copy or a wait there is a bubble in the pipe: measured, profiles/round2_ncu_hera350.md section 7)
     // =====================================================================================================================
     for (int j = 0; j < ntiles; ++j) {
-      if (j + n_mn < ntiles) {  // phase F of tile j has retired: its MN-major pair takes tile j + n_mn
+      if (!no_f && j + n_mn < ntiles) {  // phase F of tile j has retired: its MN-major pair takes tile j + n_mn
         tc_wait(&bar_v[slot_of(j, nbuf)], par_of(j, nbuf), p.dbg, 6, j, l0);
         if (elect_one()) {
           const int sg = slot_of(j, n_mn);
@@ -525,15 +534,17 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
     const int mycol = cbase + 8 * part; // the 8 channels this thread does the arithmetic for
     const ClassSlot cs = s_cs[s];
     const int2 an = s_ant[s];
-    float loss_acc = 0.f;
+    float loss_acc = 0.f, sr_acc = 0.f, si_acc = 0.f;
     // this thread's inputs are loaded ONE TILE AHEAD (registers): their DRAM / L2 latency hides behind the previous tile's work.
     // Two register sets, the tile loop unrolled by two (no copies).
     f32x8 bufA[7], bufB[7];
     auto load_inputs = [&](int jt, f32x8 (&dst)[7]) {
       const int f0 = (mt.j0 + jt) * C::FT + mycol;
       const int o = cs.bl0 * p.nfp + f0, o0 = an.x + f0, o1 = an.y + f0;
-      dst[0] = ldg256(p.d_r + o);
-      dst[1] = ldg256(p.d_i + o);
+      if (!no_f) {
+        dst[0] = ldg256(p.d_r + o);
+        dst[1] = ldg256(p.d_i + o);
+      }
       dst[2] = ldg256(p.w + o);
       dst[3] = ldg256(g_r + o0);
       dst[4] = ldg256(g_i + o0);
@@ -563,52 +574,78 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       if (valid && j + 1 < ntiles) load_inputs(j + 1, nx);
       const uint32_t vcol = tmem + tlane + L.col_v + L.v_stride * vb + cbase;
       if (tid == 0) tc_stamp(p, j, 6);
-      tc_wait(&bar_v[vb], par_of(j, nbuf), p.dbg, 4, j, l0);
-      tc_fence_after();
-      if (tid == 0) tc_stamp(p, j, 7);
-      // V row of this thread, 16 columns: partial accumulators + the small terms, added with round-to-nearest
-      float v[16], t[16];
-      tmem_ld16(vcol, v);
-      if (npart > 1) {
-        tmem_ld16(vcol + 32, t);
+      float vr[8], vi[8];
+      if (!no_f) {
+        tc_wait(&bar_v[vb], par_of(j, nbuf), p.dbg, 4, j, l0);
+        tc_fence_after();
+        if (tid == 0) tc_stamp(p, j, 7);
+        // V row of this thread, 16 columns: partial accumulators + the small terms, added with round-to-nearest
+        float v[16], t[16];
+        tmem_ld16(vcol, v);
+        if (npart > 1) {
+          tmem_ld16(vcol + 32, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += t[i];
+        }
+        tmem_ld16(vcol + L.v_small, t);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += t[i];
-      }
-      tmem_ld16(vcol + L.v_small, t);
+        if (tid == 0) tc_stamp(p, j, 8);
+        // pair re / im: lane 2g holds v_r of group g, lane 2g + 1 its v_i; each takes 8 of the 16 channels
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += t[i];
-      if (tid == 0) tc_stamp(p, j, 8);
-      // pair re / im: lane 2g holds v_r of group g, lane 2g + 1 its v_i; each takes 8 of the 16 channels
-      float vr[8], vi[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float send = part ? v[i] : v[8 + i];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-        vr[i] = part ? recv : v[i];
-        vi[i] = part ? v[8 + i] : recv;
+        for (int i = 0; i < 8; ++i) {
+          const float send = part ? v[i] : v[8 + i];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          vr[i] = part ? recv : v[i];
+          vi[i] = part ? v[8 + i] : recv;
+        }
+      } else if (j >= nbuf) {
+        // second launch of 'sum': no phase F orders this tile behind phase B of the previous tile in this buffer
+        tc_wait(&bar_b[vb], par_of(j - nbuf, nbuf), p.dbg, 9, j, l0);
+        tc_fence_after();
       }
       float qr[8], qi[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) qr[i] = qi[i] = 0.f;
       if (valid) {
         const float *dr = in[0].v, *di = in[1].v, *ww = in[2].v, *gr0 = in[3].v, *gi0 = in[4].v, *gr1 = in[5].v, *gi1 = in[6].v;
-        float2 zz[8];
+        if (no_f) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {  // calibration.py:1593-1609, as in the other kernels
-          const float P = gr0[i] * gr1[i] + gi0[i] * gi1[i];
-          const float Q = gr0[i] * gi1[i] - gi0[i] * gr1[i];
-          const float mr = P * vr[i] + Q * vi[i];
-          const float mi = P * vi[i] - Q * vr[i];
-          const float rr = dr[i] - mr, ri = di[i] - mi;
-          loss_acc += (rr * rr + ri * ri) * ww[i];
-          const float er = -2.f * ww[i] * rr, ei = -2.f * ww[i] * ri;
-          zz[i] = make_float2(er * vr[i] + ei * vi[i], er * vi[i] - ei * vr[i]);
-          qr[i] = P * er - Q * ei;
-          qi[i] = Q * er + P * ei;
+          for (int i = 0; i < 8; ++i) {  // the regulariser's backward rows (calibration.py:1654): P w and Q w
+            qr[i] = (gr0[i] * gr1[i] + gi0[i] * gi1[i]) * ww[i];
+            qi[i] = (gr0[i] * gi1[i] - gi0[i] * gr1[i]) * ww[i];
+          }
+        } else {
+          float2 zz[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // calibration.py:1593-1609, as in the other kernels
+            const float P = gr0[i] * gr1[i] + gi0[i] * gi1[i];
+            const float Q = gr0[i] * gi1[i] - gi0[i] * gr1[i];
+            const float mr = P * vr[i] + Q * vi[i];
+            const float mi = P * vi[i] - Q * vr[i];
+            const float rr = dr[i] - mr, ri = di[i] - mi;
+            loss_acc += (rr * rr + ri * ri) * ww[i];
+            const float er = -2.f * ww[i] * rr, ei = -2.f * ww[i] * ri;
+            zz[i] = make_float2(er * vr[i] + ei * vi[i], er * vi[i] - ei * vr[i]);
+            qr[i] = P * er - Q * ei;
+            qi[i] = Q * er + P * ei;
+            if (mode == 1) {
+              sr_acc += ww[i] * mr;
+              si_acc += ww[i] * mi;
+            }
+          }
+          const size_t zo = (size_t)(cs.bl0 * p.nfp + f0);
+          float* zdst = reinterpret_cast<float*>(p.z + zo);
+          stg256(zdst, zz[0].x, zz[0].y, zz[1].x, zz[1].y, zz[2].x, zz[2].y, zz[3].x, zz[3].y);
+          stg256(zdst + 8, zz[4].x, zz[4].y, zz[5].x, zz[5].y, zz[6].x, zz[6].y, zz[7].x, zz[7].y);
+          if (mode == 1) {
+            float* ydst = reinterpret_cast<float*>(p.y + zo);
+            stg256(ydst, ww[0] * vr[0], ww[0] * vi[0], ww[1] * vr[1], ww[1] * vi[1], ww[2] * vr[2], ww[2] * vi[2], ww[3] * vr[3],
+                   ww[3] * vi[3]);
+            stg256(ydst + 8, ww[4] * vr[4], ww[4] * vi[4], ww[5] * vr[5], ww[5] * vi[5], ww[6] * vr[6], ww[6] * vi[6], ww[7] * vr[7],
+                   ww[7] * vi[7]);
+          }
         }
-        float* zdst = reinterpret_cast<float*>(p.z + (size_t)(cs.bl0 * p.nfp + f0));
-        stg256(zdst, zz[0].x, zz[0].y, zz[1].x, zz[1].y, zz[2].x, zz[2].y, zz[3].x, zz[3].y);
-        stg256(zdst + 8, zz[4].x, zz[4].y, zz[5].x, zz[5].y, zz[6].x, zz[6].y, zz[7].x, zz[7].y);
       }
       if (tid == 0) tc_stamp(p, j, 9);
       // back to rows: lane 2g needs q_r of all 16 columns, lane 2g + 1 q_i
@@ -645,7 +682,9 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
       tc_wait(bar_done, 0, p.dbg, 5, last, l0);
       tc_fence_after();
       // rows of dcpart are (re, im) pairs: lane 2g (re) takes the even vectors of both parts, lane 2g + 1 the odd ones
-      float2* dst = reinterpret_cast<float2*>(p.dcpart + (size_t)mt.seg * p.dc_plane) + cs.row0;
+      // (plain chi^2: rows of 2 floats; 'sum': rows of 4, the first launch fills floats 0-1, the second 2-3)
+      const int rs = mode ? 2 : 1;  // float2 per row
+      float2* dst = reinterpret_cast<float2*>(p.dcpart + (size_t)mt.seg * p.dc_plane) + (size_t)cs.row0 * rs + (mode == 2 ? 1 : 0);
       const int k_lo = half * (kpt / 2), k_hi = k_lo + kpt / 2;
       for (int k0 = k_lo; k0 < k_hi; k0 += 8) {
         float d8[8];
@@ -656,24 +695,36 @@ __global__ void __launch_bounds__(TcCfg::NTHR, 1) shared_tc_kernel(const TcParam
           const float keep = part ? d8[i + 1] : d8[i], send = part ? d8[i] : d8[i + 1];
           const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
           const int k = k0 + i + part;
-          if (valid && k < mt.ncomp) dst[k] = part ? make_float2(recv, keep) : make_float2(keep, recv);
+          if (valid && k < mt.ncomp) dst[(size_t)k * rs] = part ? make_float2(recv, keep) : make_float2(keep, recv);
         }
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
-    if (lane == 0) red[warp] = loss_acc;
+    for (int off = 16; off > 0; off >>= 1) {
+      loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+      sr_acc += __shfl_xor_sync(0xffffffffu, sr_acc, off);
+      si_acc += __shfl_xor_sync(0xffffffffu, si_acc, off);
+    }
+    if (lane == 0) {
+      red[warp] = loss_acc;
+      red[8 + warp] = sr_acc;
+      red[16 + warp] = si_acc;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && mode != 2) {  // (the second launch of 'sum' has no sums of its own)
     tc_stamp(p, 0, 22);
-    double a = 0.0;
-    for (int w8 = 0; w8 < 8; ++w8) a += (double)red[w8];
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int w8 = 0; w8 < 8; ++w8) {
+      a += (double)red[w8];
+      b += (double)red[8 + w8];
+      c += (double)red[16 + w8];
+    }
     double* dst = p.partials + (size_t)blockIdx.x * 4;
     dst[0] = a;
-    dst[1] = 0.0;
-    dst[2] = 0.0;
+    dst[1] = b;
+    dst[2] = c;
   }
   if (mma_warp) {
     tc_fence_after();
