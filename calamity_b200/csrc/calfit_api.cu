@@ -1400,6 +1400,10 @@ int calb2_plan_create(const calb2_plan_desc* d, calb2_plan** out) {
     long long tc_off = 0;
     for (auto& ci : pl->classes) {
       if (!pl->tc_enabled || (ci.nmembers < tc_min && ci.kpt <= 128)) ci.tc = false;
+      if (ci.tc) {  // the layout must fit the SM: 512 TMEM columns, 227 KB of shared memory (1 KB of it static)
+        const TcLayout L = tc_layout(ci.kpt);
+        if (L.col_qlo + 32 * L.nbuf > 512 || L.total + 1024 > 227u * 1024u) ci.tc = false;
+      }
       if (ci.tc) {
         ci.tc_off = tc_off;
         tc_off += (long long)pl->ntiles_c * 4 * ci.kpt * SHARED_FT;
