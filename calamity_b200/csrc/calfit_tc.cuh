@@ -1,5 +1,5 @@
-// Tensor-core shape of the shared-basis pass (sm_100a: tcgen05 + TMEM), for basis classes of <= 208 vectors, plain chi^2,
-// single-baseline slots.  Same work item as calfit_shared.cuh -- 64 groups of ONE class through a range of 32-channel tiles --
+// Tensor-core shape of the shared-basis pass (sm_100a: tcgen05 + TMEM), for basis classes of <= 208 vectors, single-baseline
+// slots, both regularisations ('sum': two launches, at the end of this comment).  Same work item as calfit_shared.cuh -- 64 groups of ONE class through a range of 32-channel tiles --
 // with both contractions on the 5th-generation tensor cores as TF32 MMAs with a 3-term split (hi.hi + hi.lo + lo.hi; plain TF32
 // would break the 1e-5 loss tolerance):
 //
@@ -32,6 +32,12 @@
 // The tensor pipe executes in issue order, so B(j) reads dL/dv(j) out of its V buffer before the next phase F into that buffer
 // overwrites it.  Descriptor encodings follow cute/arch/mma_sm100_desc.hpp; every operand form used here is checked by
 // tools/tc_probe.cu.
+//
+// model_regularization = 'sum' (calibration.py:619-661, 1654): the regulariser adds two backward rows per group, P w and Q w
+// (P + iQ = g_i conj(g_j)), which depend on the gains and weights only.  shared_tc_kernel<1> is the plain pass plus y = w v (read
+// by the gain-gradient kernel) and the two model sums, with dcpart rows of four floats; shared_tc_kernel<2> runs WITHOUT phase F:
+// phase Q writes the two rows as its dL/dv, phase B contracts them into floats 2-3 of the rows.  With no phase F in between,
+// phase Q of a tile waits for phase B of the previous tile in its V buffer on a barrier of its own (b[2]).
 #pragma once
 #include "calfit_shared.cuh"
 
