@@ -424,3 +424,23 @@ def test_get_auto_weights_inverse_variance_of_smoothed_autos():
         flg = uvd.flag_array[rows, 0, :, 0]
         assert np.all(got[flg] == 0.0)
         assert np.allclose(got[~flg], np.broadcast_to(want, got.shape)[~flg], rtol=2e-3)
+
+
+def test_chunk_variables_for_lamb_cover_the_coefficients_in_chunk_order():
+    """LAMB's trust ratio is per tf.Variable; the reference holds one coefficient variable per chunk (calibration.py:560-567).
+    `chunk_coef_bounds` must cut the flat coefficient vector exactly at the chunk boundaries of `flatten_coeffs`."""
+    from calamity_b200 import fitter
+    from oracle.restatement import KERAS_DEFAULTS
+    from tests.helpers import mixed_problem
+
+    p = mixed_problem(nants=24, nfreqs=96, seed=3, n_dpss_bls=120, joint=((3, 9, 20), (2, 7, 12)))
+    lay = p.lay
+    b = lay.chunk_coef_bounds()
+    assert b[0] == 0 and b[-1] == lay.ncoef and np.all(np.diff(b) > 0) and len(b) - 1 == len(lay.chunks)
+    # a coefficient tensor per chunk filled with the chunk's index lands exactly in that chunk's range
+    chunks = [np.full((ch["nvecs"], ch["ngrps"], 1, 1), float(c)) for c, ch in enumerate(lay.chunks)]
+    flat = lay.flatten_coeffs(chunks)
+    for c in range(len(lay.chunks)):
+        assert np.all(flat[b[c] : b[c + 1]] == c)
+    # the product's LAMB defaults are the oracle's (tensorflow_addons.optimizers.LAMB)
+    assert fitter.KERAS_DEFAULTS["LAMB"] == KERAS_DEFAULTS["LAMB"] and fitter.OPTIMIZER_IDS["LAMB"] == 8

@@ -139,3 +139,27 @@ def test_keras_nadam_and_ftrl_closed_forms():
         acc = acc_new
         opt.apply([q], [g.copy()], [False])
         np.testing.assert_allclose(q, expect, rtol=1e-12)
+
+
+def test_lamb_closed_form_and_per_variable_ratio():
+    """tensorflow_addons LAMB (calibration.py:15, 26): after the bias correction the first update is g / (|g| + eps) (+ weight
+    decay), scaled per VARIABLE by ||w|| / ||update||; a zero variable or a zero update takes ratio 1."""
+    from oracle.restatement import KerasOptimizer
+
+    lr, eps, wd = 0.01, 1e-6, 0.05
+    g = [np.array([0.3, -2.0, 1e-3]), np.array([5.0, 5.0])]
+    p = [np.array([1.0, -1.0, 0.5]), np.array([0.0, 0.0])]
+    opt = KerasOptimizer("LAMB", learning_rate=lr, weight_decay=wd)
+    q = [x.copy() for x in p]
+    opt.apply(q, [x.copy() for x in g], [False, False])
+    for v in range(2):
+        upd = g[v] / (np.abs(g[v]) + eps) + wd * p[v]
+        wn, un = np.linalg.norm(p[v]), np.linalg.norm(upd)
+        ratio = wn / un if wn > 0 and un > 0 else 1.0
+        np.testing.assert_allclose(q[v], p[v] - lr * ratio * upd, rtol=1e-12)
+    assert np.linalg.norm(p[1]) == 0 and not np.allclose(q[1], 0)  # ratio 1 for the zero variable, it still moves
+    # the ratio couples the elements of ONE variable only: the same numbers as a single variable give another step
+    opt1 = KerasOptimizer("LAMB", learning_rate=lr, weight_decay=wd)
+    q1 = np.concatenate(p)
+    opt1.apply([q1], [np.concatenate(g)], [False])
+    assert not np.allclose(q1, np.concatenate(q))
