@@ -180,3 +180,29 @@ def test_plan_info_counts_the_deduplication(native_built):
     lay2.blocks = [b.copy() for b in lay2.blocks]
     lay2._finalize()
     assert len(set(lay2.group_class.tolist())) == len(distinct)
+
+
+@pytest.mark.parametrize("reg", [None, "sum"])
+def test_graph_replay_of_the_tensor_core_pass_is_bit_identical(native_built, reg):
+    """Small problems replay a captured CUDA graph of iterations (calb2_fit, use_graph): with the tensor-core kernel(s), the
+    streaming items forked onto the second stream and the forked coefficient update inside the capture, the replay must give
+    the bits of the kernel-by-kernel launch."""
+    from calamity_b200 import synth
+    from calamity_b200.fitter import FitPlan
+
+    prob = synth.make("hera37", init_gain_scatter=0.02, coeff_error=0.05)
+    outs = []
+    for graph in (False, True):
+        plan = FitPlan(prob.layout(), device=0)
+        assert plan.info["n_tc_ctas"] > 0  # classes of >= 16 groups: the default sends them to the tensor cores
+        plan.set_integration(prob.data_r, prob.data_i, prob.wgts)
+        plan.set_gains(prob.g0_r, prob.g0_i)
+        plan.set_coeffs(prob.c0_r, prob.c0_i)
+        pr, pi = plan.prior_sums(prob.data_r, prob.data_i)
+        hist, _ = plan.fit(optimizer="Adamax", maxsteps=100, tol=0.0, learning_rate=1e-2, model_regularization=reg,
+                           prior_r_sum=0.9 * pr, prior_i_sum=1.1 * pi, use_graph=graph)
+        outs.append((hist, plan.get_gains()[0], plan.get_coeffs()[0]))
+        plan.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    assert outs[0][0][-1] < 0.05 * outs[0][0][0]
